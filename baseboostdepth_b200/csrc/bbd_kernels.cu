@@ -1,0 +1,469 @@
+// libbbd_loss.so: sm_100a kernels and the C ABI declared in include/bbd_loss.h.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+// (see baseboostdepth_b200/build.py).  No torch types cross this file's boundary.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "bbd_ops.cuh"
+#include "bbd_smooth.cuh"
+#include "bbd_tile.cuh"
+
+namespace bbd {
+
+// Tile shape of the fused loss: 32x16 target pixels per block of 256 threads.  With two
+// warped candidates the block needs ~83 KB of shared memory -> 2 blocks per SM.
+using Cfg = TileCfg<32, 16, 256>;
+
+static thread_local char g_err[256] = "";
+
+static int fail(int code, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s", what);
+  return code;
+}
+static int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// identity pre-pass
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(Cfg::NT) ident_kernel(const bbd_ident_args a) {
+  extern __shared__ float smem[];
+  IdentSmem<Cfg> sm;
+  sm.carve(smem);
+  const int tid = threadIdx.x;
+  TileId t = make_tile(blockIdx.x, blockIdx.y, blockIdx.z, a.batch, a.height, a.width, Cfg::TW, Cfg::TH);
+  const int32_t* hdr = a.tab.hdr + (size_t)t.b * 4;
+  const int n_id = hdr[1];
+  const float* noise = a.noise[hdr[2]] + (size_t)hdr[3] * a.height * a.width;
+  id_load<Cfg>(a, a.target + (size_t)t.b * 3 * a.height * a.width, sm.tgt, t, tid);
+  __syncthreads();
+  id_target_stats<Cfg>(a, sm, tid);
+  for (int j = 0; j < n_id; ++j) {
+    const int32_t* e = a.tab.ident + ((size_t)t.b * BBD_MAX_IDENT + j) * 2;
+    const float* src = a.frames[e[0]] + (size_t)e[1] * 3 * a.height * a.width;
+    id_load<Cfg>(a, src, sm.src, t, tid);
+    __syncthreads();
+    id_candidate<Cfg>(a, sm, t, j, noise, tid);
+    __syncthreads();
+  }
+  id_store<Cfg>(a, sm, t, tid);
+}
+
+// ------------------------------------------------------------------------------------------
+// fused reprojection loss
+// ------------------------------------------------------------------------------------------
+template <bool GRAD>
+__global__ void __launch_bounds__(Cfg::NT) reproj_kernel(const bbd_reproj_args a) {
+  extern __shared__ float smem[];
+  ReprojSmem<Cfg> sm;
+  sm.carve(smem, a.max_rep);
+  const int tid = threadIdx.x;
+  TileId t = make_tile(blockIdx.x, blockIdx.y, blockIdx.z, a.batch, a.height, a.width, Cfg::TW, Cfg::TH);
+  const int n_rep = a.tab.hdr[(size_t)t.b * 4];
+
+  rp_load_target<Cfg>(a, sm, t, tid);
+  __syncthreads();
+  rp_target_stats<Cfg>(a, sm, t, tid);
+  for (int k = 0; k < n_rep; ++k) {
+    rp_warp<Cfg>(a, sm, t, k, tid);
+    __syncthreads();
+    rp_stats<Cfg>(a, sm, t, k, tid);
+  }
+  const float part = rp_select<Cfg>(a, sm, t, n_rep, tid);
+  red_park<Cfg, 1>(sm.red, tid, &part);
+  __syncthreads();
+  red_level1<Cfg, 1>(sm.red, tid);
+  __syncthreads();
+  red_level2<Cfg, 1>(sm.red, tid, a.loss_part + ((size_t)t.s * a.batch + t.b) * t.ntiles + t.tile);
+
+  if (GRAD) {
+    for (int k = 0; k < BBD_MAX_REP; ++k) {
+      float* out = a.gpose_part + ((((size_t)t.s * a.batch + t.b) * BBD_MAX_REP + k) * t.ntiles + t.tile) * 12;
+      if (k >= n_rep || !sm.anywin[k]) {  // block-uniform
+        if (tid < 12) out[tid] = 0.0f;
+        continue;
+      }
+      float gP[12];
+      rp_backward<Cfg>(a, sm, t, k, tid, gP);
+      red_park<Cfg, 12>(sm.red, tid, gP);
+      __syncthreads();
+      red_level1<Cfg, 12>(sm.red, tid);
+      __syncthreads();
+      red_level2<Cfg, 12>(sm.red, tid, out);
+    }
+    rp_store_gdepth<Cfg>(a, sm, t, tid);
+  }
+}
+
+// Sum the per-tile partials in a fixed order.  grid.x = S * (1 + num_pose); block 0..S-1 -> loss.
+__global__ void __launch_bounds__(128) reproj_finalize_kernel(const bbd_reproj_args a, float* loss, float* gpose, int ntiles) {
+  __shared__ float red[128];
+  const int tid = threadIdx.x;
+  const int S = a.num_scales;
+  if ((int)blockIdx.x < S) {
+    const int s = blockIdx.x;
+    const float* p = a.loss_part + (size_t)s * a.batch * ntiles;
+    float acc = 0.0f;
+    for (int i = tid; i < a.batch * ntiles; i += 128) acc += p[i];
+    red[tid] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      float tot = 0.0f;
+      for (int i = 0; i < 128; ++i) tot += red[i];
+      loss[s] = tot / ((float)a.batch * (float)a.height * (float)a.width);
+    }
+    return;
+  }
+  if (!gpose) return;
+  // one block per (scale, pose row): find the (sample, candidate) that uses this pose
+  const int idx = blockIdx.x - S, s = idx / a.num_pose, pose = idx % a.num_pose;
+  float acc = 0.0f;  // thread tid<12 accumulates component tid
+  for (int b = 0; b < a.batch; ++b) {
+    const int n_rep = a.tab.hdr[(size_t)b * 4];
+    for (int k = 0; k < n_rep; ++k) {
+      if (a.tab.rep[((size_t)b * BBD_MAX_REP + k) * 4 + 2] != pose) continue;
+      const float* p = a.gpose_part + (((size_t)s * a.batch + b) * BBD_MAX_REP + k) * ntiles * 12;
+      if (tid < 12)
+        for (int tI = 0; tI < ntiles; ++tI) acc += p[(size_t)tI * 12 + tid];
+    }
+  }
+  if (tid < 12) gpose[((size_t)s * a.num_pose + pose) * 12 + tid] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// smoothness
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SM_NT) smooth_stage1_kernel(const SmoothArgs a) {
+  __shared__ float red[SM_NT + SM_NT / 16];
+  const int lvl = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  if (chunk >= sm_chunks(a.h[lvl], a.w[lvl])) return;
+  sm_park(red, tid, sm_stage1_thread(a, lvl, b, chunk, tid));
+  __syncthreads();
+  sm_l1(red, tid);
+  __syncthreads();
+  if (tid == 0) sm_slot(a, lvl, b, 0)[chunk] = sm_l2(red);
+}
+
+__global__ void __launch_bounds__(SM_NT) smooth_stage2_kernel(const SmoothArgs a) {
+  __shared__ float red[SM_NT + SM_NT / 16];
+  __shared__ float mean_s;
+  const int lvl = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  if (chunk >= sm_chunks(a.h[lvl], a.w[lvl])) return;
+  if (tid == 0) mean_s = sm_sample_mean(a, lvl, b);
+  __syncthreads();
+  float out[3];
+  sm_stage2_thread(a, lvl, b, chunk, tid, mean_s, out);
+  for (int k = 0; k < 3; ++k) {
+    sm_park(red, tid, out[k]);
+    __syncthreads();
+    sm_l1(red, tid);
+    __syncthreads();
+    if (tid == 0) sm_slot(a, lvl, b, 1 + k)[chunk] = sm_l2(red);
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(SM_NT) smooth_stage3_kernel(const SmoothArgs a) {
+  __shared__ float red[SM_NT + SM_NT / 16];
+  __shared__ float mean_s;
+  const int lvl = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  if (chunk >= sm_chunks(a.h[lvl], a.w[lvl])) return;
+  if (tid == 0) mean_s = sm_sample_mean(a, lvl, b);
+  __syncthreads();
+  sm_stage3_thread(a, lvl, b, chunk, tid, mean_s);
+  if (b == 0 && chunk == 0) {
+    float out[2];
+    sm_loss_thread(a, lvl, tid, out);
+    float tot[2];
+    for (int k = 0; k < 2; ++k) {
+      sm_park(red, tid, out[k]);
+      __syncthreads();
+      sm_l1(red, tid);
+      __syncthreads();
+      tot[k] = sm_l2(red);
+      __syncthreads();
+    }
+    if (tid == 0) {
+      const float h = (float)a.h[lvl], w = (float)a.w[lvl], B = (float)a.batch;
+      a.loss[lvl] = tot[0] / (B * h * (w - 1.0f)) + tot[1] / (B * (h - 1.0f) * w);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// element-wise operators
+// ------------------------------------------------------------------------------------------
+__global__ void d2d_forward_kernel(const bbd_d2d_args a) {
+  const int HW = a.height * a.width;
+  const size_t total = (size_t)a.levels * a.batch * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int px = (int)(i % a.width), py = (int)((i / a.width) % a.height);
+    const int b = (int)((i / HW) % a.batch), lvl = (int)(i / ((size_t)HW * a.batch));
+    a.depth[i] = d2d_forward_px(a, lvl, b, py, px);
+  }
+}
+
+__global__ void d2d_backward_kernel(const bbd_d2d_args a) {
+  const int lvl = blockIdx.z;
+  const int h = a.h[lvl], w = a.w[lvl];
+  const size_t total = (size_t)a.batch * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ix = (int)(i % w), iy = (int)((i / w) % h), b = (int)(i / ((size_t)h * w));
+    a.gdisp[lvl][i] = d2d_backward_px(a, lvl, b, iy, ix);
+  }
+}
+
+__global__ void warp_kernel(int n, int H, int W, const float* images, const float* depth, const float* inv_K,
+                            const float* P, float* warped, float* grid) {
+  const size_t total = (size_t)n * H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int px = (int)(i % W), py = (int)((i / W) % H), b = (int)(i / ((size_t)H * W));
+    warp_px(H, W, images, depth, inv_K, P, b, py, px, warped, grid);
+  }
+}
+
+__global__ void backproject_kernel(int n, int H, int W, const float* depth, const float* inv_K, float* points) {
+  const int HW = H * W;
+  const size_t total = (size_t)n * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    backproject_px(HW, W, depth, inv_K, (int)(i / HW), (int)(i % HW), points);
+}
+
+__global__ void backproject_grad_kernel(int n, int H, int W, const float* inv_K, const float* gpoints, float* gdepth) {
+  const int HW = H * W;
+  const size_t total = (size_t)n * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    gdepth[i] = backproject_grad_px(HW, W, inv_K, gpoints, (int)(i / HW), (int)(i % HW));
+}
+
+__global__ void project_kernel(int n, int H, int W, const float* points, const float* P, float eps, float* pix) {
+  const int HW = H * W;
+  const size_t total = (size_t)n * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    project_px(H, W, points, P, eps, (int)(i / HW), (int)(i % HW), pix);
+}
+
+constexpr int PJ_CHUNK = 4096;
+// grid (chunks, n); block 256.  gP_part (n, chunks, 12)
+__global__ void __launch_bounds__(256) project_grad_kernel(int n, int H, int W, const float* points, const float* P, float eps,
+                                                           const float* gpix, float* gpoints, float* gP_part) {
+  __shared__ float red[12][256];
+  const int HW = H * W, b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  float gP[12];
+  for (int k = 0; k < 12; ++k) gP[k] = 0.0f;
+  for (int i = chunk * PJ_CHUNK + tid; i < (chunk + 1) * PJ_CHUNK && i < HW; i += 256)
+    project_grad_px(H, W, points, P, eps, gpix, b, i, gpoints, gP);
+  for (int k = 0; k < 12; ++k) red[k][tid] = gP[k];
+  __syncthreads();
+  if (tid < 12) {
+    float s = 0.0f;
+    for (int i = 0; i < 256; ++i) s += red[tid][i];
+    gP_part[((size_t)b * gridDim.x + chunk) * 12 + tid] = s;
+  }
+}
+
+__global__ void ssim_kernel(int planes, int H, int W, const float* x, const float* y, float* out) {
+  const int HW = H * W;
+  const size_t total = (size_t)planes * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pl = i / HW;
+    const int o = (int)(i % HW);
+    out[i] = ssim_px(x + pl * HW, y + pl * HW, H, W, o / W, o % W);
+  }
+}
+
+__global__ void ssim_grad_kernel(int planes, int H, int W, const float* x, const float* y, const float* gout, float* gx, float* gy) {
+  const int HW = H * W;
+  const size_t total = (size_t)planes * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pl = i / HW;
+    const int o = (int)(i % HW);
+    ssim_grad_px(x + pl * HW, y + pl * HW, gout + pl * HW, H, W, o / W, o % W, gx ? gx + pl * HW : nullptr,
+                 gy ? gy + pl * HW : nullptr);
+  }
+}
+
+static int grid_for(size_t total, int block) {
+  size_t g = (total + block - 1) / block;
+  const size_t cap = 148 * 16;  // a few resident blocks per SM, grid-stride beyond that
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+}  // namespace bbd
+
+using namespace bbd;
+
+extern "C" {
+
+int bbd_version(void) { return BBD_ABI_VERSION; }
+const char* bbd_last_error_string(void) { return g_err; }
+
+int bbd_reproj_tiles(int32_t height, int32_t width) {
+  return ((width + Cfg::TW - 1) / Cfg::TW) * ((height + Cfg::TH - 1) / Cfg::TH);
+}
+
+int bbd_ident_forward(const bbd_ident_args* a, bbd_stream_t stream) {
+  if (!a || !a->target || !a->ident_min || !a->tab.hdr || !a->tab.ident) return fail(BBD_E_ARG, "ident: null argument");
+  if (a->batch <= 0 || a->height < 2 || a->width < 2) return fail(BBD_E_ARG, "ident: bad size");
+  dim3 grid((a->width + Cfg::TW - 1) / Cfg::TW, (a->height + Cfg::TH - 1) / Cfg::TH, a->batch);
+  const size_t smem = IdentSmem<Cfg>::floats() * sizeof(float);
+  cudaFuncSetAttribute(ident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ident_kernel<<<grid, Cfg::NT, smem, (cudaStream_t)stream>>>(*a);
+  return check_launch("ident_kernel");
+}
+
+int bbd_reproj_fused(const bbd_reproj_args* a, bbd_stream_t stream) {
+  if (!a || !a->target || !a->depth || !a->inv_K || !a->P || !a->ident_min || !a->loss_part || !a->tab.hdr || !a->tab.rep)
+    return fail(BBD_E_ARG, "reproj: null argument");
+  if (a->need_grad && (!a->gpose_part || !a->gdepth)) return fail(BBD_E_ARG, "reproj: gradient buffers missing");
+  if (a->batch <= 0 || a->height < 2 || a->width < 2 || a->num_scales <= 0) return fail(BBD_E_ARG, "reproj: bad size");
+  if (a->max_rep < 1 || a->max_rep > BBD_MAX_REP) return fail(BBD_E_RANGE, "reproj: max_rep out of range");
+  const size_t smem = ReprojSmem<Cfg>::floats(a->max_rep) * sizeof(float);
+  if (smem > 227 * 1024) return fail(BBD_E_RANGE, "reproj: shared memory budget exceeded");
+  dim3 grid((a->width + Cfg::TW - 1) / Cfg::TW, (a->height + Cfg::TH - 1) / Cfg::TH, a->num_scales * a->batch);
+  if (a->need_grad) {
+    cudaFuncSetAttribute(reproj_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    reproj_kernel<true><<<grid, Cfg::NT, smem, (cudaStream_t)stream>>>(*a);
+  } else {
+    cudaFuncSetAttribute(reproj_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    reproj_kernel<false><<<grid, Cfg::NT, smem, (cudaStream_t)stream>>>(*a);
+  }
+  return check_launch("reproj_kernel");
+}
+
+int bbd_reproj_finalize(const bbd_reproj_args* a, float* loss, float* gpose, bbd_stream_t stream) {
+  if (!a || !loss || !a->loss_part) return fail(BBD_E_ARG, "finalize: null argument");
+  if (gpose && !a->gpose_part) return fail(BBD_E_ARG, "finalize: no pose partials");
+  const int ntiles = bbd_reproj_tiles(a->height, a->width);
+  const int blocks = a->num_scales * (1 + (gpose ? a->num_pose : 0));
+  reproj_finalize_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(*a, loss, gpose, ntiles);
+  return check_launch("reproj_finalize_kernel");
+}
+
+size_t bbd_smooth_scratch_floats(int32_t batch, int32_t levels, const int32_t* h, const int32_t* w) {
+  int mc = 1;
+  for (int l = 0; l < levels; ++l) {
+    const int c = sm_chunks(h[l], w[l]);
+    if (c > mc) mc = c;
+  }
+  return (size_t)levels * batch * 4 * mc;
+}
+
+int bbd_smooth_fused(const bbd_smooth_args* in, bbd_stream_t stream) {
+  if (!in || !in->scratch || !in->loss) return fail(BBD_E_ARG, "smooth: null argument");
+  if (in->levels < 1 || in->levels > BBD_MAX_SCALES || in->batch <= 0) return fail(BBD_E_RANGE, "smooth: bad level count");
+  bbd_smooth_args a = *in;
+  int mc = 1;
+  for (int l = 0; l < a.levels; ++l) {
+    if (!a.disp[l] || !a.img[l] || a.h[l] < 2 || a.w[l] < 2) return fail(BBD_E_ARG, "smooth: bad level");
+    const int c = sm_chunks(a.h[l], a.w[l]);
+    if (c > mc) mc = c;
+  }
+  a.max_chunks = mc;
+  dim3 grid(mc, a.batch, a.levels);
+  smooth_stage1_kernel<<<grid, SM_NT, 0, (cudaStream_t)stream>>>(a);
+  smooth_stage2_kernel<<<grid, SM_NT, 0, (cudaStream_t)stream>>>(a);
+  smooth_stage3_kernel<<<grid, SM_NT, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("smooth kernels");
+}
+
+int bbd_disp_to_depth_forward(const bbd_d2d_args* a, bbd_stream_t stream) {
+  if (!a || !a->depth) return fail(BBD_E_ARG, "d2d forward: null argument");
+  if (a->levels < 1 || a->levels > BBD_MAX_SCALES) return fail(BBD_E_RANGE, "d2d: bad level count");
+  for (int l = 0; l < a->levels; ++l)
+    if (!a->disp[l] || a->h[l] < 1 || a->w[l] < 1) return fail(BBD_E_ARG, "d2d forward: bad level");
+  const size_t total = (size_t)a->levels * a->batch * a->height * a->width;
+  d2d_forward_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*a);
+  return check_launch("d2d_forward_kernel");
+}
+
+int bbd_disp_to_depth_backward(const bbd_d2d_args* a, bbd_stream_t stream) {
+  if (!a || !a->depth || !a->gdepth || !a->gscale) return fail(BBD_E_ARG, "d2d backward: null argument");
+  if (a->levels < 1 || a->levels > BBD_MAX_SCALES) return fail(BBD_E_RANGE, "d2d: bad level count");
+  size_t most = 1;
+  for (int l = 0; l < a->levels; ++l) {
+    if (!a->gdisp[l]) return fail(BBD_E_ARG, "d2d backward: bad level");
+    if (a->height % a->h[l] || a->width % a->w[l]) return fail(BBD_E_RANGE, "d2d backward: non-integer scale factor");
+    const size_t n = (size_t)a->batch * a->h[l] * a->w[l];
+    if (n > most) most = n;
+  }
+  dim3 grid(grid_for(most, 128), 1, a->levels);
+  d2d_backward_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*a);
+  return check_launch("d2d_backward_kernel");
+}
+
+int bbd_warp_forward(int32_t n, int32_t height, int32_t width, const float* images, const float* depth, const float* inv_K,
+                     const float* P, float* warped, float* grid, bbd_stream_t stream) {
+  if (!images || !depth || !inv_K || !P || !warped) return fail(BBD_E_ARG, "warp: null argument");
+  if (n == 0) return 0;
+  warp_kernel<<<grid_for((size_t)n * height * width, 256), 256, 0, (cudaStream_t)stream>>>(n, height, width, images, depth,
+                                                                                         inv_K, P, warped, grid);
+  return check_launch("warp_kernel");
+}
+
+int bbd_backproject_forward(int32_t n, int32_t height, int32_t width, const float* depth, const float* inv_K, float* points,
+                            bbd_stream_t stream) {
+  if (!depth || !inv_K || !points) return fail(BBD_E_ARG, "backproject: null argument");
+  if (n == 0) return 0;
+  backproject_kernel<<<grid_for((size_t)n * height * width, 256), 256, 0, (cudaStream_t)stream>>>(n, height, width, depth,
+                                                                                                inv_K, points);
+  return check_launch("backproject_kernel");
+}
+
+int bbd_backproject_backward(int32_t n, int32_t height, int32_t width, const float* inv_K, const float* gpoints,
+                             float* gdepth, bbd_stream_t stream) {
+  if (!inv_K || !gpoints || !gdepth) return fail(BBD_E_ARG, "backproject backward: null argument");
+  if (n == 0) return 0;
+  backproject_grad_kernel<<<grid_for((size_t)n * height * width, 256), 256, 0, (cudaStream_t)stream>>>(
+      n, height, width, inv_K, gpoints, gdepth);
+  return check_launch("backproject_grad_kernel");
+}
+
+int bbd_project_forward(int32_t n, int32_t height, int32_t width, const float* points, const float* P, float eps,
+                        float* pix, bbd_stream_t stream) {
+  if (!points || !P || !pix) return fail(BBD_E_ARG, "project: null argument");
+  if (n == 0) return 0;
+  project_kernel<<<grid_for((size_t)n * height * width, 256), 256, 0, (cudaStream_t)stream>>>(n, height, width, points, P,
+                                                                                            eps, pix);
+  return check_launch("project_kernel");
+}
+
+int bbd_project_chunks(int32_t height, int32_t width) { return (height * width + PJ_CHUNK - 1) / PJ_CHUNK; }
+
+int bbd_project_backward(int32_t n, int32_t height, int32_t width, const float* points, const float* P, float eps,
+                         const float* gpix, float* gpoints, float* gP_part, bbd_stream_t stream) {
+  if (!points || !P || !gpix || !gpoints || !gP_part) return fail(BBD_E_ARG, "project backward: null argument");
+  if (n == 0) return 0;
+  dim3 grid(bbd_project_chunks(height, width), n);
+  project_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, height, width, points, P, eps, gpix, gpoints, gP_part);
+  return check_launch("project_grad_kernel");
+}
+
+int bbd_ssim_forward(int32_t n, int32_t channels, int32_t height, int32_t width, const float* x, const float* y, float* out,
+                     bbd_stream_t stream) {
+  if (!x || !y || !out) return fail(BBD_E_ARG, "ssim: null argument");
+  if (height < 2 || width < 2) return fail(BBD_E_RANGE, "ssim: reflection padding needs at least 2 pixels");
+  if (n * channels == 0) return 0;
+  ssim_kernel<<<grid_for((size_t)n * channels * height * width, 256), 256, 0, (cudaStream_t)stream>>>(n * channels, height,
+                                                                                                    width, x, y, out);
+  return check_launch("ssim_kernel");
+}
+
+int bbd_ssim_backward(int32_t n, int32_t channels, int32_t height, int32_t width, const float* x, const float* y,
+                      const float* gout, float* gx, float* gy, bbd_stream_t stream) {
+  if (!x || !y || !gout) return fail(BBD_E_ARG, "ssim backward: null argument");
+  if (n * channels == 0 || (!gx && !gy)) return 0;
+  ssim_grad_kernel<<<grid_for((size_t)n * channels * height * width, 128), 128, 0, (cudaStream_t)stream>>>(
+      n * channels, height, width, x, y, gout, gx, gy);
+  return check_launch("ssim_grad_kernel");
+}
+
+}  // extern "C"

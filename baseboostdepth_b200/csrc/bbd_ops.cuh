@@ -1,0 +1,198 @@
+// Per-element host/device bodies of the small operators around the fused loss:
+// disparity -> depth (and back), on-demand warping, and the module-level
+// BackprojectDepth / Project3D / SSIM operators.  Kernels in bbd_kernels.cu map one
+// thread to one element (grid-stride); tests/emu loops over elements on the CPU.
+#pragma once
+#include "bbd_common.cuh"
+
+namespace bbd {
+
+// ---- F.interpolate(bilinear, align_corners=False) source taps (ATen UpSample.h) ----------
+struct Lerp {
+  int i0, i1;
+  float l0, l1;
+};
+BBD_HD Lerp up_taps(int o, int in_size, int out_size) {
+  const float scale = (float)in_size / (float)out_size;
+  float src = scale * ((float)o + 0.5f) - 0.5f;
+  if (src < 0.0f) src = 0.0f;
+  Lerp t;
+  t.i0 = (int)src;
+  t.i1 = t.i0 + ((t.i0 < in_size - 1) ? 1 : 0);
+  t.l1 = src - (float)t.i0;
+  t.l0 = 1.0f - t.l1;
+  return t;
+}
+
+BBD_HD float d2d_up(const float* d, int w, const Lerp& ty, const Lerp& tx) {
+  const float* r0 = d + (size_t)ty.i0 * w;
+  const float* r1 = d + (size_t)ty.i1 * w;
+  return ty.l0 * (tx.l0 * r0[tx.i0] + tx.l1 * r0[tx.i1]) + ty.l1 * (tx.l0 * r1[tx.i0] + tx.l1 * r1[tx.i1]);
+}
+
+// one full-resolution pixel: upsample + disp_to_depth (layers.py:13-22)
+BBD_HD float d2d_forward_px(const bbd_d2d_args& a, int lvl, int b, int oy, int ox) {
+  const int h = a.h[lvl], w = a.w[lvl];
+  const float* d = a.disp[lvl] + (size_t)b * h * w;
+  const float up = d2d_up(d, w, up_taps(oy, h, a.height), up_taps(ox, w, a.width));
+  if (a.sql) return up;
+  return div_(1.0f, add(a.min_disp, mul(a.disp_span, up)));
+}
+
+// one low-resolution disparity pixel: gather d(loss)/d(disp) from the full-res pixels it fed
+BBD_HD float d2d_backward_px(const bbd_d2d_args& a, int lvl, int b, int iy, int ix) {
+  const int h = a.h[lvl], w = a.w[lvl], H = a.height, W = a.width;
+  const float* gd = a.gdepth + ((size_t)lvl * a.batch + b) * H * W;
+  const float* dep = a.depth + ((size_t)lvl * a.batch + b) * H * W;
+  const float span = a.disp_span;
+  const int fy = H / h, fx = W / w;
+  // outputs whose source coordinate lies within one input pixel of (iy, ix)
+  int oy_lo = iy * fy - fy, oy_hi = iy * fy + 2 * fy;
+  int ox_lo = ix * fx - fx, ox_hi = ix * fx + 2 * fx;
+  if (oy_lo < 0) oy_lo = 0;
+  if (ox_lo < 0) ox_lo = 0;
+  if (oy_hi > H) oy_hi = H;
+  if (ox_hi > W) ox_hi = W;
+  float acc = 0.0f;
+  for (int oy = oy_lo; oy < oy_hi; ++oy) {
+    const Lerp ty = up_taps(oy, h, H);
+    const float wy = (ty.i0 == iy ? ty.l0 : 0.0f) + (ty.i1 == iy ? ty.l1 : 0.0f);
+    if (wy == 0.0f) continue;
+    float row = 0.0f;
+    for (int ox = ox_lo; ox < ox_hi; ++ox) {
+      const Lerp tx = up_taps(ox, w, W);
+      const float wx = (tx.i0 == ix ? tx.l0 : 0.0f) + (tx.i1 == ix ? tx.l1 : 0.0f);
+      if (wx == 0.0f) continue;
+      const size_t o = (size_t)oy * W + ox;
+      float g = gd[o];
+      if (!a.sql) g *= -span * dep[o] * dep[o];
+      row += wx * g;
+    }
+    acc += wy * row;
+  }
+  acc *= a.gscale[lvl];
+  if (a.gsmooth[lvl]) acc += a.gsmooth_scale[lvl] * a.gsmooth[lvl][((size_t)b * h + iy) * w + ix];
+  return acc;
+}
+
+// ---- on-demand warp (trainer.py:434-442): one output pixel, three channels ----------------
+BBD_HD void warp_px(int H, int W, const float* images, const float* depth, const float* inv_K, const float* P,
+                    int n, int py, int px, float* warped, float* grid) {
+  Cam cam;
+  load_cam(cam, inv_K + (size_t)n * 16, P + (size_t)n * 12);
+  Sample s;
+  const size_t o = (size_t)py * W + px;
+  project_pixel(cam, px, py, depth[(size_t)n * H * W + o], W, H, s);
+  Taps tp;
+  make_taps(s, W, H, tp);
+  const float* src = images + (size_t)n * 3 * H * W;
+  float* dst = warped + (size_t)n * 3 * H * W;
+  for (int c = 0; c < 3; ++c) dst[(size_t)c * H * W + o] = tap_channel(src + (size_t)c * H * W, tp);
+  if (grid) {
+    grid[((size_t)n * 2) * H * W + o] = mul(sub(div_(s.ux, (float)(W - 1)), 0.5f), 2.0f);
+    grid[((size_t)n * 2 + 1) * H * W + o] = mul(sub(div_(s.uy, (float)(H - 1)), 0.5f), 2.0f);
+  }
+}
+
+// ---- BackprojectDepth (layers.py:160-167) --------------------------------------------------
+BBD_HD void backproject_px(int HW, int W, const float* depth, const float* inv_K, int n, int i, float* points) {
+  const float* ik = inv_K + (size_t)n * 16;
+  const float x = (float)(i % W), y = (float)(i / W);
+  const float d = depth[(size_t)n * HW + i];
+  float* p = points + (size_t)n * 4 * HW + i;
+  p[0] = mul(d, fma_(ik[2], 1.0f, fma_(ik[1], y, mul(ik[0], x))));
+  p[HW] = mul(d, fma_(ik[6], 1.0f, fma_(ik[5], y, mul(ik[4], x))));
+  p[2 * (size_t)HW] = mul(d, fma_(ik[10], 1.0f, fma_(ik[9], y, mul(ik[8], x))));
+  p[3 * (size_t)HW] = 1.0f;
+}
+BBD_HD float backproject_grad_px(int HW, int W, const float* inv_K, const float* gpoints, int n, int i) {
+  const float* ik = inv_K + (size_t)n * 16;
+  const float x = (float)(i % W), y = (float)(i / W);
+  const float* g = gpoints + (size_t)n * 4 * HW + i;
+  const float rx = fma_(ik[2], 1.0f, fma_(ik[1], y, mul(ik[0], x)));
+  const float ry = fma_(ik[6], 1.0f, fma_(ik[5], y, mul(ik[4], x)));
+  const float rz = fma_(ik[10], 1.0f, fma_(ik[9], y, mul(ik[8], x)));
+  return g[0] * rx + g[HW] * ry + g[2 * (size_t)HW] * rz;
+}
+
+// ---- Project3D (layers.py:181-195) ----------------------------------------------------------
+BBD_HD void project_px(int H, int W, const float* points, const float* P, float eps, int n, int i, float* pix) {
+  const int HW = H * W;
+  const float* p = P + (size_t)n * 12;
+  const float* q = points + (size_t)n * 4 * HW + i;
+  const float X = q[0], Y = q[HW], Z = q[2 * (size_t)HW], Wc = q[3 * (size_t)HW];
+  const float cx = fma_(p[3], Wc, fma_(p[2], Z, fma_(p[1], Y, mul(p[0], X))));
+  const float cy = fma_(p[7], Wc, fma_(p[6], Z, fma_(p[5], Y, mul(p[4], X))));
+  const float cz = fma_(p[11], Wc, fma_(p[10], Z, fma_(p[9], Y, mul(p[8], X))));
+  const float zz = add(cz, eps);
+  pix[((size_t)n * 2) * HW + i] = mul(sub(div_(div_(cx, zz), (float)(W - 1)), 0.5f), 2.0f);
+  pix[((size_t)n * 2 + 1) * HW + i] = mul(sub(div_(div_(cy, zz), (float)(H - 1)), 0.5f), 2.0f);
+}
+// gradient wrt points (written) and wrt P (accumulated into gP[12] by the caller's thread)
+BBD_HD void project_grad_px(int H, int W, const float* points, const float* P, float eps, const float* gpix, int n, int i,
+                            float* gpoints, float gP[12]) {
+  const int HW = H * W;
+  const float* p = P + (size_t)n * 12;
+  const float* q = points + (size_t)n * 4 * HW + i;
+  const float X[4] = {q[0], q[HW], q[2 * (size_t)HW], q[3 * (size_t)HW]};
+  float c[3];
+  for (int r = 0; r < 3; ++r) c[r] = fma_(p[4 * r + 3], X[3], fma_(p[4 * r + 2], X[2], fma_(p[4 * r + 1], X[1], mul(p[4 * r], X[0]))));
+  const float zz = add(c[2], eps);
+  const float inv = 1.0f / zz;
+  const float gux = gpix[((size_t)n * 2) * HW + i] * 2.0f / (float)(W - 1);
+  const float guy = gpix[((size_t)n * 2 + 1) * HW + i] * 2.0f / (float)(H - 1);
+  const float gc[3] = {gux * inv, guy * inv, -(gux * c[0] + guy * c[1]) * inv * inv};
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 4; ++k) gP[4 * r + k] += gc[r] * X[k];
+  float* g = gpoints + (size_t)n * 4 * HW + i;
+  for (int k = 0; k < 4; ++k) g[(size_t)k * HW] = p[k] * gc[0] + p[4 + k] * gc[1] + p[8 + k] * gc[2];
+}
+
+// ---- SSIM operator (layers.py:235-249), any channel count, reads global memory -------------
+BBD_HD float plane_at(const float* p, int H, int W, int y, int x) { return p[(size_t)reflect1(y, H) * W + reflect1(x, W)]; }
+
+BBD_HD void ssim_window(const float* x, const float* y, int H, int W, int py, int px, WinX& wx, WinY& wy) {
+  float sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+  bool first = true;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      const float a = plane_at(x, H, W, py + dy, px + dx), b = plane_at(y, H, W, py + dy, px + dx);
+      if (first) { sx = a; sy = b; sxx = mul(a, a); syy = mul(b, b); sxy = mul(a, b); first = false; }
+      else { sx = add(sx, a); sy = add(sy, b); sxx = add(sxx, mul(a, a)); syy = add(syy, mul(b, b)); sxy = add(sxy, mul(a, b)); }
+    }
+  wx.sx = sx; wx.sxx = sxx; wx.sxy = sxy;
+  wy = target_stats(sy, syy);
+}
+
+BBD_HD float ssim_px(const float* x, const float* y, int H, int W, int py, int px) {
+  WinX wx; WinY wy; SsimParts q;
+  ssim_window(x, y, H, W, py, px, wx, wy);
+  return ssim_channel(wx, wy, q);
+}
+
+// gradient at pixel (py,px) of plane x (and y): gather over the windows that contain it
+BBD_HD void ssim_grad_px(const float* x, const float* y, const float* gout, int H, int W, int py, int px, float* gx, float* gy) {
+  float ax = 0, bx = 0, cx = 0, ay = 0, by = 0, cy = 0;
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int cyy = py + dy;
+    if (cyy < 0 || cyy >= H) continue;
+    const float my = ((py == 1 && dy == -1) || (py == H - 2 && dy == 1)) ? 2.0f : 1.0f;
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int cxx = px + dx;
+      if (cxx < 0 || cxx >= W) continue;
+      const float m = my * (((px == 1 && dx == -1) || (px == W - 2 && dx == 1)) ? 2.0f : 1.0f);
+      WinX wx; WinY wy; SsimParts q;
+      ssim_window(x, y, H, W, cyy, cxx, wx, wy);
+      ssim_channel(wx, wy, q);
+      const float g = gout[(size_t)cyy * W + cxx] * m;
+      float a, b, c;
+      if (gx) { ssim_coefs(q, wy, g, a, b, c); ax += a; bx += b; cx += c; }
+      if (gy) { ssim_coefs_y(q, wy, g, a, b, c); ay += a; by += b; cy += c; }
+    }
+  }
+  const size_t o = (size_t)py * W + px;
+  if (gx) gx[o] = ax + bx * x[o] + cx * y[o];
+  if (gy) gy[o] = ay + by * y[o] + cy * x[o];
+}
+
+}  // namespace bbd

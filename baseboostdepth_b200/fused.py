@@ -1,0 +1,225 @@
+"""Fused view-synthesis loss: one autograd node over the C ABI.
+
+``fused_losses`` evaluates, for all scales of a step, what the reference spreads
+over ``generate_images_pred`` (``trainer.py:444-475``) and ``compute_losses``
+(``trainer.py:488-570``): disparity -> depth, identity pre-pass, warp + SSIM/L1 +
+per-pixel minimum, smoothness -- forward *and* backward -- in seven kernel
+launches, and returns the per-scale reprojection means and smoothness terms as
+differentiable tensors.  Gradients flow to the disparities and to the packed
+projection matrices ``P = (K @ T)[:, :3, :]``.
+
+Because every loss term is a mean with a weight known in advance, the kernels
+produce the unit gradients during the forward launch; ``backward`` only folds
+the upstream scalars in while gathering the full-resolution depth gradient
+down to the disparity resolution.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .plan import LossPlan
+
+
+def _tables(plan: LossPlan, device):
+    cache = getattr(plan, "_dev_tables", None)
+    if cache is None or cache[0] != str(device):
+        hdr = torch.from_numpy(plan.hdr).to(device)
+        rep = torch.from_numpy(plan.rep_tab).to(device)
+        ident = torch.from_numpy(plan.ident_tab).to(device)
+        cache = (str(device), hdr, rep, ident)
+        plan._dev_tables = cache
+    t = _lib.Tables()
+    t.hdr, t.rep, t.ident = cache[1].data_ptr(), cache[2].data_ptr(), cache[3].data_ptr()
+    return t
+
+
+def _frame_ptrs(plan: LossPlan, frames: Dict, height, width):
+    arr = (C.c_void_p * _lib.MAX_FRAMES)()
+    keep = []
+    for slot, f in enumerate(plan.frames):
+        t = frames[f]
+        need = max(plan.stack_row[f], default=-1) + 1
+        if t.shape[0] < need or tuple(t.shape[1:]) != (3, height, width):
+            raise ValueError(f"frame stack {f!r} has shape {tuple(t.shape)}, need >= {need} rows of (3,{height},{width})")
+        t = t.contiguous()
+        keep.append(t)
+        arr[slot] = t.data_ptr() if t.numel() else None
+    return arr, keep
+
+
+class _FusedLoss(torch.autograd.Function):
+    """(P, disp_0..disp_{S-1}) -> (reproj[S], smooth[S]); everything else is closed over."""
+
+    @staticmethod
+    def forward(ctx, cfg, P, *disps):
+        be: _lib.Backend = cfg["backend"]
+        plan: LossPlan = cfg["plan"]
+        target, frames, inv_K = cfg["target"], cfg["frames"], cfg["inv_K"]
+        noise, pyramid = cfg["noise"], cfg["pyramid"]
+        B, _, H, W = target.shape
+        S = len(disps)
+        dev = target.device
+        need_grad = bool(cfg["need_grad"])
+        f32 = dict(device=dev, dtype=torch.float32)
+        be.check_device(target, inv_K, P, *disps, *pyramid, *noise.values(), *frames.values())
+        assert plan.batch == B and P.shape == (plan.n_pose, 3, 4), (P.shape, plan.n_pose)
+        assert S <= _lib.MAX_SCALES
+
+        disps_c = [d.detach().contiguous() for d in disps]
+        Pc = P.detach().contiguous()
+        target = target.contiguous()
+        inv_K = inv_K.contiguous()
+        tab = _tables(plan, dev)
+        frame_arr, keep = _frame_ptrs(plan, frames, H, W)
+
+        # 1. disparity -> depth at full resolution for every scale
+        depth = torch.empty(S, B, H, W, **f32)
+        d2d = _lib.D2DArgs()
+        d2d.batch, d2d.levels, d2d.height, d2d.width = B, S, H, W
+        d2d.min_disp = 1 / cfg["max_depth"]
+        d2d.disp_span = 1 / cfg["min_depth"] - 1 / cfg["max_depth"]
+        d2d.sql = int(cfg["sql"])
+        for l, d in enumerate(disps_c):
+            d2d.h[l], d2d.w[l] = d.shape[2], d.shape[3]
+            d2d.disp[l] = d.data_ptr()
+        d2d.depth = depth.data_ptr()
+        be.call("disp_to_depth_forward", C.byref(d2d))
+
+        # 2. identity pre-pass (once per step)
+        ident_min = torch.empty(B, H, W, **f32)
+        want_winner = bool(cfg["want_winner"])
+        ident_arg = torch.empty(B, H, W, device=dev, dtype=torch.uint8) if want_winner else None
+        ia = _lib.IdentArgs()
+        ia.batch, ia.height, ia.width, ia.no_ssim = B, H, W, int(cfg["no_ssim"])
+        ia.target = target.data_ptr()
+        ia.frames = frame_arr
+        for slot, g in enumerate(plan.groups):
+            n = noise[g].contiguous()
+            keep.append(n)
+            assert n.shape[0] == len(plan.group_members[g]) and tuple(n.shape[-2:]) == (H, W)
+            ia.noise[slot] = n.data_ptr()
+        ia.noise_scale = float(cfg["noise_scale"])
+        ia.tab = tab
+        ia.ident_min = ident_min.data_ptr()
+        ia.ident_arg = _lib.ptr(ident_arg)
+        be.call("ident_forward", C.byref(ia))
+
+        # 3. fused warp + photometric + min (+ gradients)
+        ntiles = be.value("reproj_tiles", H, W)
+        loss_part = torch.empty(S, B, ntiles, **f32)
+        gpose_part = torch.empty(S, B, _lib.MAX_REP, ntiles, 12, **f32) if need_grad else None
+        gdepth = torch.empty(S, B, H, W, **f32) if need_grad else None
+        winner = torch.empty(S, B, H, W, device=dev, dtype=torch.uint8) if want_winner else None
+        ra = _lib.ReprojArgs()
+        ra.batch, ra.height, ra.width, ra.num_scales = B, H, W, S
+        ra.no_ssim, ra.need_grad, ra.max_rep, ra.num_pose = int(cfg["no_ssim"]), int(need_grad), plan.max_rep, plan.n_pose
+        ra.target, ra.frames, ra.depth = target.data_ptr(), frame_arr, depth.data_ptr()
+        ra.inv_K, ra.P, ra.ident_min, ra.tab = inv_K.data_ptr(), Pc.data_ptr(), ident_min.data_ptr(), tab
+        ra.loss_part, ra.gpose_part, ra.gdepth = loss_part.data_ptr(), _lib.ptr(gpose_part), _lib.ptr(gdepth)
+        ra.winner, ra.ident_arg = _lib.ptr(winner), _lib.ptr(ident_arg)
+        timers = cfg.get("timers")
+        if timers is not None and be.cuda:
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            be.call("reproj_fused", C.byref(ra))
+            t1.record()
+            timers["reproj_fused"] = (t0, t1)
+        else:
+            be.call("reproj_fused", C.byref(ra))
+
+        # 4. fixed-order reduction of the per-tile partials
+        reproj = torch.empty(S, **f32)
+        gpose = torch.empty(S, plan.n_pose, 3, 4, **f32) if need_grad else None
+        be.call("reproj_finalize", C.byref(ra), C.c_void_p(reproj.data_ptr()), C.c_void_p(_lib.ptr(gpose)))
+
+        # 5. smoothness on the disparity pyramid
+        sa = _lib.SmoothArgs()
+        sa.batch, sa.levels = B, S
+        gsm = []
+        smooth_src = disps_c
+        for l, d in enumerate(smooth_src):
+            img = pyramid[l].contiguous()
+            keep.append(img)
+            assert img.shape[0] == B and img.shape[-2:] == d.shape[-2:], (img.shape, d.shape)
+            sa.h[l], sa.w[l] = d.shape[2], d.shape[3]
+            sa.disp[l], sa.img[l] = d.data_ptr(), img.data_ptr()
+            if need_grad:
+                g = torch.empty_like(d)
+                gsm.append(g)
+                sa.gdisp[l] = g.data_ptr()
+        hs = (C.c_int32 * S)(*[d.shape[2] for d in smooth_src])
+        ws = (C.c_int32 * S)(*[d.shape[3] for d in smooth_src])
+        scratch = torch.empty(max(1, be.value("smooth_scratch_floats", B, S, hs, ws)), **f32)
+        smooth = torch.empty(S, **f32)
+        sa.scratch, sa.loss = scratch.data_ptr(), smooth.data_ptr()
+        be.call("smooth_fused", C.byref(sa))
+
+        ctx.cfg = cfg
+        ctx.d2d = d2d
+        ctx.keep = (disps_c, depth, gdepth, gpose, gsm)
+        ctx.aux = {"depth": depth, "ident_min": ident_min, "ident_arg": ident_arg, "winner": winner}
+        cfg["aux"] = ctx.aux
+        return reproj, smooth
+
+    @staticmethod
+    def backward(ctx, g_reproj, g_smooth):
+        cfg = ctx.cfg
+        be: _lib.Backend = cfg["backend"]
+        disps_c, depth, gdepth, gpose, gsm = ctx.keep
+        if gdepth is None:
+            raise RuntimeError("bbd: fused loss was evaluated with need_grad=False")
+        g_reproj = g_reproj.contiguous().float()
+        g_smooth = g_smooth.contiguous().float()
+        gP = torch.einsum("s,spij->pij", g_reproj, gpose) if ctx.needs_input_grad[1] else None
+        d2d = ctx.d2d
+        gdisps = [torch.empty_like(d) for d in disps_c]
+        d2d.gdepth = gdepth.data_ptr()
+        d2d.gscale = g_reproj.data_ptr()
+        d2d.gsmooth_scale = g_smooth.data_ptr()
+        for l, g in enumerate(gdisps):
+            d2d.gdisp[l] = g.data_ptr()
+            d2d.gsmooth[l] = gsm[l].data_ptr()
+        be.call("disp_to_depth_backward", C.byref(d2d))
+        return (None, gP) + tuple(gdisps)
+
+
+def fused_losses(plan: LossPlan, target: torch.Tensor, frames: Dict, disps: Sequence[torch.Tensor],
+                 inv_K: torch.Tensor, P: torch.Tensor, noise: Dict, pyramid: Sequence[torch.Tensor], *,
+                 min_depth=0.1, max_depth=100.0, no_ssim=False, sql=False, noise_scale=1.0,
+                 want_winner=False, need_grad: Optional[bool] = None, backend: Optional[_lib.Backend] = None,
+                 timers: Optional[dict] = None):
+    """Per-scale ``(reproj[S], smooth[S], aux)`` of the view-synthesis loss.
+
+    ``frames[f]`` are the compacted ``("color", f, 0)`` stacks, ``disps[s]`` the network
+    disparities, ``P`` the packed ``(K @ T)[:, :3, :]`` rows in ``plan.pose_slices()`` order,
+    ``noise[g]`` the per-group tie-break planes (multiplied by ``noise_scale`` in-kernel),
+    ``pyramid[s]`` the target colour pyramid ``("color", 0, s)``.
+    ``aux`` exposes ``depth`` (S,B,H,W) and, with ``want_winner``, the argmin planes.
+    """
+    be = backend if backend is not None else _lib.cuda_backend()
+    if need_grad is None:
+        need_grad = torch.is_grad_enabled() and (P.requires_grad or any(d.requires_grad for d in disps))
+    cfg = dict(backend=be, plan=plan, target=target, frames=frames, inv_K=inv_K, noise=noise,
+               pyramid=list(pyramid), min_depth=min_depth, max_depth=max_depth, no_ssim=no_ssim, sql=sql,
+               noise_scale=noise_scale, want_winner=want_winner, need_grad=need_grad, timers=timers)
+    reproj, smooth = _FusedLoss.apply(cfg, P, *disps)
+    return reproj, smooth, cfg["aux"]
+
+
+def pack_poses(plan: LossPlan, K: torch.Tensor, T: Dict, T_err: Optional[Dict] = None) -> torch.Tensor:
+    """Pack ``P = (K[:n] @ T_f)[:, :3, :]`` of every frame in ``plan.pose_slices()`` order.
+
+    ``K[:n]`` (first n rows, not the selected samples' rows) is what the reference pairs
+    with a frame's poses (``trainer.py:431``, ``layers.py:182``).
+    """
+    rows = []
+    for f, is_err, lo, hi in plan.pose_slices():
+        src = T_err if is_err else T
+        Tf = src[f]
+        assert Tf.shape[0] == hi - lo, (f, Tf.shape, hi - lo)
+        rows.append(torch.matmul(K[: hi - lo], Tf)[:, :3, :])
+    return torch.cat(rows, 0) if rows else K.new_zeros(0, 3, 4)

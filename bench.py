@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the view-synthesis loss hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # the sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...    # reference algorithm on host cores
+
+One *step* = one pass of the hot path over one synthetic batch: disparity -> depth,
+identity pre-pass, warp + SSIM/L1 + per-pixel minimum over every source, smoothness,
+forward and backward (gradients to every disparity scale and to the poses).
+Metric: warped px-pairs per second, whole job over all ranks.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "warped px-pairs/s fwd+bwd (photometric loss)"
+UNIT = "px-pairs/s"
+DEFAULT_WORKLOAD = "kitti_640x192_b12_pm1"   # BASELINE.json configs[1]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(name):
+    from baseboostdepth_b200.synthetic import WORKLOADS
+    B, H, W, baselines, trimin, decomp = WORKLOADS[name]
+    return dict(batch=B, height=H, width=W, baselines=list(baselines), trimin=trimin, decomp=decomp)
+
+
+def make_opt(cfg):
+    from types import SimpleNamespace
+    return SimpleNamespace(height=cfg["height"], width=cfg["width"], scales=[0, 1, 2, 3], min_depth=0.1,
+                           max_depth=100.0, disparity_smoothness=1e-3, no_ssim=False, trimin=cfg["trimin"],
+                           decomp=cfg["decomp"], pose_error=5.5, SQL=False, batch_size=cfg["batch"])
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_run(cfg, steps, warmup, sample_batch=None):
+    """The reference algorithm (oracle port, plain PyTorch ops) on the host cores.
+
+    Returns (px-pairs/s, seconds per step, sample description, threads)."""
+    from baseboostdepth_b200.plan import build_plan
+    from baseboostdepth_b200.synthetic import make_batch, make_noise, px_pairs
+    from oracle import loss_path as O
+
+    c = dict(cfg)
+    if sample_batch is not None and sample_batch < c["batch"]:
+        c["baselines"] = c["baselines"][:sample_batch]
+        c["batch"] = sample_batch
+    opt = make_opt(c)
+    inputs, outputs, params = make_batch(seed=1234, device="cpu", pose_error=5.5, **c)
+    plan = build_plan(inputs["ordering"], trimin=c["trimin"], decomp=c["decomp"])
+    noise = make_noise(plan, c["height"], c["width"])
+    pairs = px_pairs(plan, c["height"], c["width"], 4)
+    # use every host thread unless that is slower than one (oversubscribed / quota-limited hosts)
+    probe = {}
+    for n in sorted({os.cpu_count() or 1, 1}, reverse=True):
+        torch.set_num_threads(n)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            O.run(inputs, dict(outputs), opt, noise, num_scales=4)
+        probe[n] = time.perf_counter() - t0
+    threads = min(probe, key=probe.get)
+    torch.set_num_threads(threads)
+    times = []
+    for it in range(warmup + steps):
+        for p in params.values():
+            p.grad = None
+        fresh = {k: v for k, v in outputs.items() if k[0] in ("disp", "cam_T_cam", "cam_T_cam_error")}
+        # poses must be rebuilt from their leaves each step (the graph is consumed by backward)
+        from baseboostdepth_b200.geometry import transformation_from_parameters
+        for k in list(fresh):
+            if k[0] == "cam_T_cam" and ("axisangle", k[2]) in params:
+                fresh[k] = transformation_from_parameters(params[("axisangle", k[2])], params[("translation", k[2])],
+                                                          invert=(k[2] < 0))
+        t0 = time.perf_counter()
+        out, _ = O.run(inputs, fresh, opt, noise, num_scales=4)
+        out["loss"].backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    sample = (f"{c['batch']} of {cfg['batch']} samples of the workload, all scales and sources, "
+              f"{steps} timed steps after {warmup} warm-up")
+    return pairs / sec, sec, sample, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = workload(args.workload)
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 3))
+    value, sec, sample, threads = cpu_reference_run(cfg, steps, warmup, sample_batch=2)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "device": "host CPU",
+                       "note": "oracle port of the reference's PyTorch loss path (reference is Python; "
+                               "/root/reference cannot travel to the GPU box)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    from baseboostdepth_b200 import _lib
+    from baseboostdepth_b200.geometry import transformation_from_parameters
+    from baseboostdepth_b200.synthetic import algorithmic_bytes, make_batch, make_noise, px_pairs
+    from baseboostdepth_b200.trainer import loss_step, plan_for
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cfg = workload(args.workload)
+    opt = make_opt(cfg)
+    H, W = cfg["height"], cfg["width"]
+    inputs, outputs, params = make_batch(seed=1234 + rank, device=dev, pose_error=5.5, **cfg)
+    plan = plan_for(inputs["ordering"], cfg["trimin"], cfg["decomp"],
+                    inputs[("color", "s", 0)].shape[0] if ("color", "s", 0) in inputs else None)
+    noise = {g: n.to(dev) for g, n in make_noise(plan, H, W, seed=4321 + rank).items()}
+    pairs = px_pairs(plan, H, W, 4)
+    abytes = algorithmic_bytes(plan, H, W, [0, 1, 2, 3])
+    be = _lib.cuda_backend()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def rebuild_poses():
+        for k in list(outputs):
+            if k[0] == "cam_T_cam" and ("axisangle", k[2]) in params:
+                outputs[k] = transformation_from_parameters(params[("axisangle", k[2])], params[("translation", k[2])],
+                                                            invert=(k[2] < 0))
+
+    timers = {}
+
+    def step():
+        rebuild_poses()
+        losses = loss_step(inputs, outputs, opt, plan, noise=noise, num_scales=4, timers=timers)
+        losses["loss"].backward()
+        return losses["loss"]
+
+    # ---- device-resident timing ------------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        for p in params.values():
+            p.grad = None
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    be.launches = 0
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ev = []
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        for p in params.values():
+            p.grad = None
+        flush.zero_()
+        timers.clear()
+        ev[i][0].record()
+        step()
+        ev[i][1].record()
+        kernel_ev.append(timers.get("reproj_fused"))
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = be.launches
+    step_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    kern_ms = sum(a.elapsed_time(b) for a, b in kernel_ev if a is not None) / max(1, len(kernel_ev))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end: pinned host inputs -> H2D -> fused loss fwd+bwd -> D2H loss -------------
+    e2e = None
+    if not args.no_e2e:
+        host = {k: v.detach().cpu().pin_memory() for k, v in inputs.items() if torch.is_tensor(v)}
+        host_par = {k: v.detach().cpu().pin_memory() for k, v in params.items()}
+        host_noise = {g: n.cpu().pin_memory() for g, n in noise.items()}
+        h2d = sum(t.numel() * t.element_size() for d in (host, host_par, host_noise) for t in d.values())
+
+        def e2e_step():
+            gin = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            gin["ordering"] = inputs["ordering"]
+            gpar = {k: v.to(dev, non_blocking=True).requires_grad_(True) for k, v in host_par.items()}
+            gnoise = {g: n.to(dev, non_blocking=True) for g, n in host_noise.items()}
+            gout = {k: v for k, v in gpar.items() if k[0] == "disp"}
+            for k in outputs:
+                if k[0] == "cam_T_cam" and ("axisangle", k[2]) in gpar:
+                    gout[k] = transformation_from_parameters(gpar[("axisangle", k[2])], gpar[("translation", k[2])],
+                                                             invert=(k[2] < 0))
+                    if cfg["decomp"]:
+                        te = gout[k].clone().detach()
+                        te[:, :3, 3:] /= 5.5
+                        gout[("cam_T_cam_error", 0, k[2])] = te
+                elif k[0] == "cam_T_cam":
+                    gout[k] = outputs[k]
+                    if cfg["decomp"]:
+                        gout[("cam_T_cam_error", 0, k[2])] = outputs[("cam_T_cam_error", 0, k[2])]
+            losses = loss_step(gin, gout, opt, plan, noise=gnoise, num_scales=4)
+            losses["loss"].backward()
+            return float(losses["loss"])          # device -> host read of the step's result
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        n_e2e = max(5, min(args.steps, 30))
+        t_e2e = 0.0
+        for _ in range(n_e2e):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e2e_step()
+            torch.cuda.synchronize()
+            t_e2e += time.perf_counter() - t0
+        barrier()
+        e2e_ms = t_e2e / n_e2e * 1e3
+    else:
+        e2e_ms, h2d = None, 0
+
+    # ---- max over ranks ------------------------------------------------------------------------
+    vals = torch.tensor([step_ms, kern_ms, e2e_ms or 0.0, wall * 1e3 / args.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    step_ms, kern_ms, e2e_ms_max, wall_ms = (float(v) for v in vals.cpu())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (
+            6650.0, "fallback (B200_PROFILING.md)")
+        achieved = abytes["reproj"] / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        except (OSError, ValueError):
+            pass
+        line = {
+            "metric": METRIC, "value": pairs * world / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "batch_per_gpu": cfg["batch"], "height": H, "width": W,
+                       "scales": 4, "px_pairs_per_step_per_gpu": pairs, "sharding": f"batch x{world}, no data-path collective",
+                       "l2": "flushed between steps (256 MiB memset, outside the per-step events)",
+                       "timing": "CUDA events per step on the launch stream, mean over steps, max over ranks",
+                       "wall_ms_per_step_incl_flush": wall_ms},
+            "roofline": {"bound": "hbm", "kernel": "reproj_kernel<true>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "peak_source": peak_src, "kernel_ms": kern_ms,
+                         "algorithmic_bytes_per_launch": abytes["reproj"],
+                         "step_algorithmic_bytes": abytes["total"],
+                         "step_frac": abytes["total"] / (step_ms * 1e-3) / 1e9 / peak},
+            "clocks": clocks, "gpu_launches": launches,
+        }
+        if e2e_ms is not None:
+            line["e2e"] = {"value": pairs * world / (e2e_ms_max * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_max,
+                           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+        if not args.no_cpu_baseline and world == 1:
+            v, sec, sample, threads = cpu_reference_run(cfg, steps=2, warmup=1, sample_batch=4)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                                    "s_per_step": sec}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,192 @@
+/*
+ * bbd_loss.h -- C ABI of libbbd_loss.so: the B200-native view-synthesis loss.
+ *
+ * The reference (kieran514/baseboostdepth) is pure PyTorch and ships no native
+ * interface; what this library replaces is the chain of ATen calls issued by
+ *   layers.py:160-167   BackprojectDepth.forward
+ *   layers.py:181-195   Project3D.forward
+ *   trainer.py:439,442  F.grid_sample(bilinear, border, align_corners=True)
+ *   layers.py:235-249   SSIM.forward
+ *   trainer.py:477-486  Trainer.compute_reprojection_loss
+ *   trainer.py:508-557  identity terms, noise, per-pixel minimum (+ x_min_opt :983-1100)
+ *   layers.py:203-216   get_smooth_loss (+ mean-normalisation trainer.py:560-562)
+ *   trainer.py:456-460  F.interpolate(disp) + disp_to_depth (layers.py:13-22)
+ * Each entry point below cites the reference lines it stands in for.
+ *
+ * Contract
+ *   - All pointers are DEVICE pointers to fp32 (or the stated integer type),
+ *     contiguous NCHW unless said otherwise; the caller allocates every
+ *     input, output, gradient and scratch buffer.  The library never
+ *     allocates or frees device memory and keeps no global state besides the
+ *     last error string (thread-local).
+ *   - All work is enqueued on `stream`; nothing synchronises; every call is
+ *     CUDA-graph capturable.  One process drives one GPU.
+ *   - Return value: 0 on success, a cudaError_t (>0) if a launch failed, or a
+ *     negative BBD_E_* code for a bad argument.  Nothing throws, nothing exits.
+ *   - There is no CPU implementation behind these symbols.
+ */
+#ifndef BBD_LOSS_H_
+#define BBD_LOSS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BBD_ABI_VERSION 1
+#define BBD_MAX_FRAMES 16 /* image stacks: frames -7..7 and 's' */
+#define BBD_MAX_GROUPS 8  /* noise stacks: one per baseline group */
+#define BBD_MAX_REP 12    /* warped candidates per target sample (x_min_opt, decomp) */
+#define BBD_MAX_IDENT 6   /* identity candidates per target sample */
+#define BBD_MAX_SCALES 4
+
+#define BBD_E_ARG (-1)   /* null pointer / non-positive size */
+#define BBD_E_RANGE (-2) /* table entry or size outside the supported range */
+
+typedef void* bbd_stream_t; /* cudaStream_t */
+
+/* Per-batch index tables built on the host (baseboostdepth_b200/plan.py):
+ *   hdr   (B,4)  int32: n_rep, n_ident, noise stack, noise row
+ *   rep   (B,BBD_MAX_REP,4)   int32: frame stack, stack row, pose row, K row
+ *   ident (B,BBD_MAX_IDENT,2) int32: frame stack, stack row
+ * They replace the boolean-list masks of Trainer.valid_frames_trimin
+ * (trainer.py:888-981) and the tensor copies of trainer.py:426-429,501-540. */
+typedef struct bbd_tables {
+  const int32_t* hdr;
+  const int32_t* rep;
+  const int32_t* ident;
+} bbd_tables;
+
+/* ---- identity pre-pass ---------------------------------------------------
+ * trainer.py:501-523: identity_reprojection_losses[f] = compute_reprojection_loss(
+ * color[f], color[0]) for every source of a sample, + noise, then the minimum
+ * over them in candidate order.  Writes ident_min (B,H,W) = min_j(ident_j +
+ * noise*noise_scale) and ident_arg (B,H,W) uint8 = first j attaining it. */
+typedef struct bbd_ident_args {
+  int32_t batch, height, width;
+  int32_t no_ssim; /* options.py:173 */
+  const float* target;                   /* ("color",0,0): (B,3,H,W) */
+  const float* frames[BBD_MAX_FRAMES];   /* ("color",f,0) stacks: (n_f,3,H,W) */
+  const float* noise[BBD_MAX_GROUPS];    /* randn planes per group: (n_g,1,H,W) */
+  float noise_scale;                     /* 1e-5 for raw randn, 1 if pre-scaled */
+  bbd_tables tab;
+  float* ident_min;
+  uint8_t* ident_arg;
+} bbd_ident_args;
+int bbd_ident_forward(const bbd_ident_args* a, bbd_stream_t stream);
+
+/* ---- fused reprojection loss, forward + backward in one pass -------------
+ * trainer.py:444-475 (generate_images_pred) and :525-557 (compute_losses) for
+ * all scales of a step: back-project, project with P = (K@T)[:3], bilinear
+ * border warp of every candidate source, SSIM + L1 mix, per-pixel minimum
+ * against ident_min, and -- because the loss is a mean with a known weight --
+ * the gradient of sum_s mean(to_optimise_s) with respect to depth and P.
+ * Outputs are per-tile partial sums; bbd_reproj_finalize reduces them in a
+ * fixed order (deterministic, no float atomics). */
+typedef struct bbd_reproj_args {
+  int32_t batch, height, width, num_scales;
+  int32_t no_ssim;
+  int32_t need_grad;  /* 0: forward only (validation / logging) */
+  int32_t max_rep;    /* max n_rep over the batch (sizes shared memory) */
+  int32_t num_pose;   /* rows of P */
+  const float* target;                 /* (B,3,H,W) */
+  const float* frames[BBD_MAX_FRAMES]; /* stacks (n_f,3,H,W) */
+  const float* depth;                  /* (S,B,H,W) outputs[("depth",0,s)] */
+  const float* inv_K;                  /* (B,4,4) inputs[("inv_K",0)] */
+  const float* P;                      /* (num_pose,3,4) = (K@T)[:, :3, :] */
+  const float* ident_min;              /* (B,H,W) from bbd_ident_forward */
+  bbd_tables tab;
+  float* loss_part;   /* (S,B,tiles) partial sums of to_optimise */
+  float* gpose_part;  /* (S,B,BBD_MAX_REP,tiles,12) partial d/dP sums; may be NULL if !need_grad */
+  float* gdepth;      /* (S,B,H,W) d mean_s / d depth_s;        may be NULL if !need_grad */
+  uint8_t* winner;    /* (S,B,H,W) argmin index in candidate order (reproj..., then ident...); may be NULL */
+  const uint8_t* ident_arg; /* (B,H,W); only read when winner != NULL */
+} bbd_reproj_args;
+int bbd_reproj_tiles(int32_t height, int32_t width); /* tiles per (scale, sample) */
+int bbd_reproj_fused(const bbd_reproj_args* a, bbd_stream_t stream);
+/* loss (S) = sum(loss_part)/(B*H*W); gpose (S,num_pose,3,4) = sum over tiles. */
+int bbd_reproj_finalize(const bbd_reproj_args* a, float* loss, float* gpose, bbd_stream_t stream);
+
+/* ---- warped images on demand ----------------------------------------------
+ * outputs[("color",f,s)] for logging (trainer.py:722-726): same projection and
+ * sampling as bbd_reproj_fused for one frame stack; pose rows / K rows are the
+ * first n rows (the trainer's [:frame_size] slices, trainer.py:431-432). */
+int bbd_warp_forward(int32_t n, int32_t height, int32_t width, const float* images, /* (n,3,H,W) */
+                     const float* depth,                                           /* (n,1,H,W) */
+                     const float* inv_K, const float* P, float* warped,             /* (n,3,H,W) */
+                     float* grid /* (n,2,H,W) normalised coords, may be NULL */, bbd_stream_t stream);
+
+/* ---- edge-aware smoothness, forward + backward ----------------------------
+ * trainer.py:560-563 + layers.py:203-216 for every pyramid level of a step:
+ * d = disp / (mean_hw(disp) + 1e-7); loss = mean|dx d|e^{-mean_c|dx I|} + same in y.
+ * Three enqueued stages (sample means; per-pixel terms and the coupling sum;
+ * final gradient), each covering all levels.  loss[l] and gdisp[l] = d loss[l] / d disp_l
+ * are unweighted; the caller applies disparity_smoothness / 2^scale (trainer.py:564). */
+typedef struct bbd_smooth_args {
+  int32_t batch, levels;
+  int32_t h[BBD_MAX_SCALES], w[BBD_MAX_SCALES];
+  const float* disp[BBD_MAX_SCALES]; /* (B,1,h,w) outputs[("disp",s)] */
+  const float* img[BBD_MAX_SCALES];  /* (B,3,h,w) inputs[("color",0,s)] */
+  float* gdisp[BBD_MAX_SCALES];      /* (B,1,h,w) or NULL for forward only */
+  float* scratch;                    /* bbd_smooth_scratch_floats() floats */
+  float* loss;                       /* (levels) */
+  int32_t max_chunks;                /* set by the library */
+} bbd_smooth_args;
+size_t bbd_smooth_scratch_floats(int32_t batch, int32_t levels, const int32_t* h, const int32_t* w);
+int bbd_smooth_fused(const bbd_smooth_args* a, bbd_stream_t stream);
+
+/* ---- disparity -> full-resolution depth, and back ---------------------------
+ * trainer.py:456-461 for every scale of a step: F.interpolate(bilinear,
+ * align_corners=False) to (H,W), then depth = 1/(min_disp + (max_disp-min_disp)*disp)
+ * (layers.py:13-22); sql != 0 skips the conversion (opt.SQL).  The backward gathers,
+ * for every low-resolution disparity pixel, the full-resolution pixels it contributed
+ * to (no atomics) and multiplies by gscale[s] (a DEVICE array: the upstream gradient of
+ * the per-scale loss is only known on the device when autograd runs). */
+typedef struct bbd_d2d_args {
+  int32_t batch, levels, height, width;
+  int32_t h[BBD_MAX_SCALES], w[BBD_MAX_SCALES];
+  float min_disp;  /* float(1/max_depth)               (layers.py:18) */
+  float disp_span; /* float(1/min_depth - 1/max_depth) (layers.py:20, formed in double like the reference) */
+  int32_t sql;
+  const float* disp[BBD_MAX_SCALES]; /* (B,1,h,w) */
+  float* depth;                      /* (S,B,H,W) written by forward, read by backward */
+  const float* gdepth;               /* (S,B,H,W) backward only */
+  const float* gscale;               /* (S) device, backward only */
+  const float* gsmooth[BBD_MAX_SCALES]; /* (B,1,h,w) optional extra term (smoothness gradient), or NULL */
+  const float* gsmooth_scale;        /* (S) device: gdisp += gsmooth_scale[s] * gsmooth[s] */
+  float* gdisp[BBD_MAX_SCALES];      /* (B,1,h,w) backward only */
+} bbd_d2d_args;
+int bbd_disp_to_depth_forward(const bbd_d2d_args* a, bbd_stream_t stream);
+int bbd_disp_to_depth_backward(const bbd_d2d_args* a, bbd_stream_t stream);
+
+/* ---- module-level operators (tier A: trainer.py unchanged) -----------------
+ * Same maths as the layers in layers.py, one kernel each, forward and backward. */
+/* layers.py:160-167; points (n,4,HW) */
+int bbd_backproject_forward(int32_t n, int32_t height, int32_t width, const float* depth,
+                            const float* inv_K, float* points, bbd_stream_t stream);
+int bbd_backproject_backward(int32_t n, int32_t height, int32_t width, const float* inv_K,
+                             const float* gpoints, float* gdepth, bbd_stream_t stream);
+/* layers.py:181-195 after P=(K@T)[:3]; pix laid out (n,2,H,W) -- the reference returns the
+ * (n,H,W,2) permuted view of exactly this memory. */
+int bbd_project_forward(int32_t n, int32_t height, int32_t width, const float* points, const float* P,
+                        float eps, float* pix, bbd_stream_t stream);
+/* gpoints (n,4,HW); gP_part (n,chunks,12) reduced by the caller; chunks = bbd_project_chunks */
+int bbd_project_chunks(int32_t height, int32_t width);
+int bbd_project_backward(int32_t n, int32_t height, int32_t width, const float* points, const float* P,
+                         float eps, const float* gpix, float* gpoints, float* gP_part,
+                         bbd_stream_t stream);
+/* layers.py:235-249; gx / gy may be NULL */
+int bbd_ssim_forward(int32_t n, int32_t channels, int32_t height, int32_t width, const float* x,
+                     const float* y, float* out, bbd_stream_t stream);
+int bbd_ssim_backward(int32_t n, int32_t channels, int32_t height, int32_t width, const float* x,
+                      const float* y, const float* gout, float* gx, float* gy, bbd_stream_t stream);
+
+int bbd_version(void);
+const char* bbd_last_error_string(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBD_LOSS_H_ */

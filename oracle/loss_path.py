@@ -304,7 +304,7 @@ def losses(inputs, outputs, opt, masks, noise, num_scales=None):
     if opt.trimin:
         ident = _rekey(ident, masks.valid_tri_mask_reverse)
 
-    out, aux = {}, {"to_optimise": {}, "argmin": {}, "groups": groups}
+    out, aux = {}, {"to_optimise": {}, "argmin": {}, "planes": {}, "groups": groups}
     total = 0
     for s in opt.scales:
         rep = {f: reprojection_loss(outputs[("color", f, s)], target[f], opt.no_ssim) for f in frames}
@@ -317,7 +317,7 @@ def losses(inputs, outputs, opt, masks, noise, num_scales=None):
             if opt.decomp:
                 rep_d = _rekey(rep_d, masks.valid_tri_mask_reverse, skip_stereo=True)
 
-        mins, args = [], []
+        mins, args, cats = [], [], []
         for g in groups:
             if opt.trimin:
                 keys = _tri_keys(g)
@@ -329,12 +329,15 @@ def losses(inputs, outputs, opt, masks, noise, num_scales=None):
                 planes = [rep["s"], ident["s"] + noise["s"]]
             else:
                 planes = [rep[g], rep[-g], ident[g] + noise[g], ident[-g] + noise[g]]
-            val, idx = torch.min(torch.cat(planes, dim=1), dim=1)
+            stacked = torch.cat(planes, dim=1)
+            val, idx = torch.min(stacked, dim=1)
             mins.append(val)
             args.append(idx)
+            cats.append(stacked.detach())
         to_optimise = torch.cat(mins, dim=0)
         aux["to_optimise"][s] = mins
         aux["argmin"][s] = args
+        aux["planes"][s] = cats
 
         loss = to_optimise.mean()
         disp = outputs[("disp", s)]

@@ -1,0 +1,250 @@
+// TEST-ONLY host harness: steps the thread-block phases of the sm_100a kernels on the CPU.
+//
+// The device kernels in baseboostdepth_b200/csrc/bbd_kernels.cu are thin drivers around the
+// __host__ __device__ phase functions of bbd_tile.cuh / bbd_smooth.cuh / bbd_ops.cuh.  This
+// file instantiates the same phase functions with g++ and runs, for every block, each
+// phase for tid = 0..NT-1 before moving to the next (a barrier between phases), so index
+// logic, halo/reflection handling, candidate tables and the analytic gradients can be
+// checked against the oracle in the GPU-less build container.  It is never loaded by the
+// package; exported symbols are emu_* and take HOST pointers.
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../baseboostdepth_b200/csrc/bbd_ops.cuh"
+#include "../../baseboostdepth_b200/csrc/bbd_smooth.cuh"
+#include "../../baseboostdepth_b200/csrc/bbd_tile.cuh"
+
+using namespace bbd;
+using Cfg = TileCfg<32, 16, 256>;
+#define FOR_TID for (int tid = 0; tid < Cfg::NT; ++tid)
+
+extern "C" {
+
+int emu_reproj_tiles(int32_t height, int32_t width) {
+  return ((width + Cfg::TW - 1) / Cfg::TW) * ((height + Cfg::TH - 1) / Cfg::TH);
+}
+
+int emu_ident_forward(const bbd_ident_args* ap) {
+  const bbd_ident_args& a = *ap;
+  std::vector<float> smem(IdentSmem<Cfg>::floats());
+  const int gx = (a.width + Cfg::TW - 1) / Cfg::TW, gy = (a.height + Cfg::TH - 1) / Cfg::TH;
+  for (int bz = 0; bz < a.batch; ++bz)
+    for (int by = 0; by < gy; ++by)
+      for (int bx = 0; bx < gx; ++bx) {
+        IdentSmem<Cfg> sm;
+        sm.carve(smem.data());
+        TileId t = make_tile(bx, by, bz, a.batch, a.height, a.width, Cfg::TW, Cfg::TH);
+        const int32_t* hdr = a.tab.hdr + (size_t)t.b * 4;
+        const int n_id = hdr[1];
+        const float* noise = a.noise[hdr[2]] + (size_t)hdr[3] * a.height * a.width;
+        FOR_TID id_load<Cfg>(a, a.target + (size_t)t.b * 3 * a.height * a.width, sm.tgt, t, tid);
+        FOR_TID id_target_stats<Cfg>(a, sm, tid);
+        for (int j = 0; j < n_id; ++j) {
+          const int32_t* e = a.tab.ident + ((size_t)t.b * BBD_MAX_IDENT + j) * 2;
+          const float* src = a.frames[e[0]] + (size_t)e[1] * 3 * a.height * a.width;
+          FOR_TID id_load<Cfg>(a, src, sm.src, t, tid);
+          FOR_TID id_candidate<Cfg>(a, sm, t, j, noise, tid);
+        }
+        FOR_TID id_store<Cfg>(a, sm, t, tid);
+      }
+  return 0;
+}
+
+int emu_reproj_fused(const bbd_reproj_args* ap) {
+  const bbd_reproj_args& a = *ap;
+  std::vector<float> smem(ReprojSmem<Cfg>::floats(a.max_rep));
+  std::vector<float> gPs((size_t)Cfg::NT * 12);
+  const int gx = (a.width + Cfg::TW - 1) / Cfg::TW, gy = (a.height + Cfg::TH - 1) / Cfg::TH;
+  for (int bz = 0; bz < a.num_scales * a.batch; ++bz)
+    for (int by = 0; by < gy; ++by)
+      for (int bx = 0; bx < gx; ++bx) {
+        ReprojSmem<Cfg> sm;
+        sm.carve(smem.data(), a.max_rep);
+        TileId t = make_tile(bx, by, bz, a.batch, a.height, a.width, Cfg::TW, Cfg::TH);
+        const int n_rep = a.tab.hdr[(size_t)t.b * 4];
+        FOR_TID rp_load_target<Cfg>(a, sm, t, tid);
+        FOR_TID rp_target_stats<Cfg>(a, sm, t, tid);
+        for (int k = 0; k < n_rep; ++k) {
+          FOR_TID rp_warp<Cfg>(a, sm, t, k, tid);
+          FOR_TID rp_stats<Cfg>(a, sm, t, k, tid);
+        }
+        FOR_TID {
+          const float part = rp_select<Cfg>(a, sm, t, n_rep, tid);
+          red_park<Cfg, 1>(sm.red, tid, &part);
+        }
+        FOR_TID red_level1<Cfg, 1>(sm.red, tid);
+        FOR_TID red_level2<Cfg, 1>(sm.red, tid, a.loss_part + ((size_t)t.s * a.batch + t.b) * t.ntiles + t.tile);
+        if (!a.need_grad) continue;
+        for (int k = 0; k < BBD_MAX_REP; ++k) {
+          float* out = a.gpose_part + ((((size_t)t.s * a.batch + t.b) * BBD_MAX_REP + k) * t.ntiles + t.tile) * 12;
+          if (k >= n_rep || !sm.anywin[k]) {
+            for (int i = 0; i < 12; ++i) out[i] = 0.0f;
+            continue;
+          }
+          FOR_TID {
+            rp_backward<Cfg>(a, sm, t, k, tid, &gPs[(size_t)tid * 12]);
+            red_park<Cfg, 12>(sm.red, tid, &gPs[(size_t)tid * 12]);
+          }
+          FOR_TID red_level1<Cfg, 12>(sm.red, tid);
+          FOR_TID red_level2<Cfg, 12>(sm.red, tid, out);
+        }
+        FOR_TID rp_store_gdepth<Cfg>(a, sm, t, tid);
+      }
+  return 0;
+}
+
+int emu_reproj_finalize(const bbd_reproj_args* ap, float* loss, float* gpose) {
+  const bbd_reproj_args& a = *ap;
+  const int ntiles = emu_reproj_tiles(a.height, a.width);
+  for (int s = 0; s < a.num_scales; ++s) {
+    float tot = 0.0f;
+    for (int i = 0; i < a.batch * ntiles; ++i) tot += a.loss_part[(size_t)s * a.batch * ntiles + i];
+    loss[s] = tot / ((float)a.batch * (float)a.height * (float)a.width);
+  }
+  if (!gpose) return 0;
+  for (int s = 0; s < a.num_scales; ++s)
+    for (int pose = 0; pose < a.num_pose; ++pose)
+      for (int c = 0; c < 12; ++c) {
+        float acc = 0.0f;
+        for (int b = 0; b < a.batch; ++b) {
+          const int n_rep = a.tab.hdr[(size_t)b * 4];
+          for (int k = 0; k < n_rep; ++k) {
+            if (a.tab.rep[((size_t)b * BBD_MAX_REP + k) * 4 + 2] != pose) continue;
+            const float* p = a.gpose_part + (((size_t)s * a.batch + b) * BBD_MAX_REP + k) * ntiles * 12;
+            for (int tI = 0; tI < ntiles; ++tI) acc += p[(size_t)tI * 12 + c];
+          }
+        }
+        gpose[((size_t)s * a.num_pose + pose) * 12 + c] = acc;
+      }
+  return 0;
+}
+
+size_t emu_smooth_scratch_floats(int32_t batch, int32_t levels, const int32_t* h, const int32_t* w) {
+  int mc = 1;
+  for (int l = 0; l < levels; ++l) mc = sm_chunks(h[l], w[l]) > mc ? sm_chunks(h[l], w[l]) : mc;
+  return (size_t)levels * batch * 4 * mc;
+}
+
+int emu_smooth_fused(const bbd_smooth_args* in) {
+  bbd_smooth_args a = *in;
+  int mc = 1;
+  for (int l = 0; l < a.levels; ++l) mc = sm_chunks(a.h[l], a.w[l]) > mc ? sm_chunks(a.h[l], a.w[l]) : mc;
+  a.max_chunks = mc;
+  std::vector<float> red(SM_NT + SM_NT / 16);
+  auto block_sum = [&](std::vector<float>& vals) {
+    for (int tid = 0; tid < SM_NT; ++tid) sm_park(red.data(), tid, vals[tid]);
+    for (int tid = 0; tid < SM_NT; ++tid) sm_l1(red.data(), tid);
+    return sm_l2(red.data());
+  };
+  std::vector<float> v(SM_NT), v3(3 * SM_NT);
+  for (int lvl = 0; lvl < a.levels; ++lvl)
+    for (int b = 0; b < a.batch; ++b)
+      for (int c = 0; c < sm_chunks(a.h[lvl], a.w[lvl]); ++c) {
+        for (int tid = 0; tid < SM_NT; ++tid) v[tid] = sm_stage1_thread(a, lvl, b, c, tid);
+        sm_slot(a, lvl, b, 0)[c] = block_sum(v);
+      }
+  for (int lvl = 0; lvl < a.levels; ++lvl)
+    for (int b = 0; b < a.batch; ++b) {
+      const float mean = sm_sample_mean(a, lvl, b);
+      for (int c = 0; c < sm_chunks(a.h[lvl], a.w[lvl]); ++c) {
+        for (int tid = 0; tid < SM_NT; ++tid) {
+          float out[3];
+          sm_stage2_thread(a, lvl, b, c, tid, mean, out);
+          for (int k = 0; k < 3; ++k) v3[k * SM_NT + tid] = out[k];
+        }
+        for (int k = 0; k < 3; ++k) {
+          for (int tid = 0; tid < SM_NT; ++tid) v[tid] = v3[k * SM_NT + tid];
+          sm_slot(a, lvl, b, 1 + k)[c] = block_sum(v);
+        }
+      }
+    }
+  for (int lvl = 0; lvl < a.levels; ++lvl) {
+    for (int b = 0; b < a.batch; ++b) {
+      const float mean = sm_sample_mean(a, lvl, b);
+      for (int c = 0; c < sm_chunks(a.h[lvl], a.w[lvl]); ++c)
+        for (int tid = 0; tid < SM_NT; ++tid) sm_stage3_thread(a, lvl, b, c, tid, mean);
+    }
+    float tot[2];
+    for (int k = 0; k < 2; ++k) {
+      for (int tid = 0; tid < SM_NT; ++tid) {
+        float out[2];
+        sm_loss_thread(a, lvl, tid, out);
+        v[tid] = out[k];
+      }
+      tot[k] = block_sum(v);
+    }
+    const float h = (float)a.h[lvl], w = (float)a.w[lvl], B = (float)a.batch;
+    a.loss[lvl] = tot[0] / (B * h * (w - 1.0f)) + tot[1] / (B * (h - 1.0f) * w);
+  }
+  return 0;
+}
+
+int emu_disp_to_depth_forward(const bbd_d2d_args* ap) {
+  const bbd_d2d_args& a = *ap;
+  const int HW = a.height * a.width;
+  for (int lvl = 0; lvl < a.levels; ++lvl)
+    for (int b = 0; b < a.batch; ++b)
+      for (int i = 0; i < HW; ++i)
+        a.depth[((size_t)lvl * a.batch + b) * HW + i] = d2d_forward_px(a, lvl, b, i / a.width, i % a.width);
+  return 0;
+}
+
+int emu_disp_to_depth_backward(const bbd_d2d_args* ap) {
+  const bbd_d2d_args& a = *ap;
+  for (int lvl = 0; lvl < a.levels; ++lvl) {
+    const int h = a.h[lvl], w = a.w[lvl];
+    for (int b = 0; b < a.batch; ++b)
+      for (int i = 0; i < h * w; ++i) a.gdisp[lvl][(size_t)b * h * w + i] = d2d_backward_px(a, lvl, b, i / w, i % w);
+  }
+  return 0;
+}
+
+int emu_warp_forward(int32_t n, int32_t H, int32_t W, const float* images, const float* depth, const float* inv_K,
+                     const float* P, float* warped, float* grid) {
+  for (int b = 0; b < n; ++b)
+    for (int i = 0; i < H * W; ++i) warp_px(H, W, images, depth, inv_K, P, b, i / W, i % W, warped, grid);
+  return 0;
+}
+
+int emu_backproject_forward(int32_t n, int32_t H, int32_t W, const float* depth, const float* inv_K, float* points) {
+  for (int b = 0; b < n; ++b)
+    for (int i = 0; i < H * W; ++i) backproject_px(H * W, W, depth, inv_K, b, i, points);
+  return 0;
+}
+int emu_backproject_backward(int32_t n, int32_t H, int32_t W, const float* inv_K, const float* gpoints, float* gdepth) {
+  for (int b = 0; b < n; ++b)
+    for (int i = 0; i < H * W; ++i) gdepth[(size_t)b * H * W + i] = backproject_grad_px(H * W, W, inv_K, gpoints, b, i);
+  return 0;
+}
+int emu_project_forward(int32_t n, int32_t H, int32_t W, const float* points, const float* P, float eps, float* pix) {
+  for (int b = 0; b < n; ++b)
+    for (int i = 0; i < H * W; ++i) project_px(H, W, points, P, eps, b, i, pix);
+  return 0;
+}
+int emu_project_chunks(int32_t, int32_t) { return 1; }
+int emu_project_backward(int32_t n, int32_t H, int32_t W, const float* points, const float* P, float eps, const float* gpix,
+                         float* gpoints, float* gP_part) {
+  for (int b = 0; b < n; ++b) {
+    float gP[12] = {0};
+    for (int i = 0; i < H * W; ++i) project_grad_px(H, W, points, P, eps, gpix, b, i, gpoints, gP);
+    for (int k = 0; k < 12; ++k) gP_part[(size_t)b * 12 + k] = gP[k];
+  }
+  return 0;
+}
+int emu_ssim_forward(int32_t n, int32_t ch, int32_t H, int32_t W, const float* x, const float* y, float* out) {
+  for (size_t pl = 0; pl < (size_t)n * ch; ++pl)
+    for (int i = 0; i < H * W; ++i) out[pl * H * W + i] = ssim_px(x + pl * H * W, y + pl * H * W, H, W, i / W, i % W);
+  return 0;
+}
+int emu_ssim_backward(int32_t n, int32_t ch, int32_t H, int32_t W, const float* x, const float* y, const float* gout,
+                      float* gx, float* gy) {
+  for (size_t pl = 0; pl < (size_t)n * ch; ++pl)
+    for (int i = 0; i < H * W; ++i)
+      ssim_grad_px(x + pl * H * W, y + pl * H * W, gout + pl * H * W, H, W, i / W, i % W, gx ? gx + pl * H * W : nullptr,
+                   gy ? gy + pl * H * W : nullptr);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,39 @@
+"""Run the fused path (CUDA library or the CPU emulation harness) on a trainer-style batch."""
+from __future__ import annotations
+
+import os
+import subprocess
+
+import torch
+
+from baseboostdepth_b200 import _lib
+from baseboostdepth_b200.trainer import loss_step, materialise_warps, plan_for
+
+EMU_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+_EMU = None
+
+
+def emu_backend() -> _lib.Backend:
+    """Compile (if stale) and load tests/emu/libbbd_emu.so -- the kernels' phase code run on the CPU."""
+    global _EMU
+    if _EMU is None:
+        so, src = os.path.join(EMU_DIR, "libbbd_emu.so"), os.path.join(EMU_DIR, "bbd_emu.cpp")
+        csrc = os.path.join(os.path.dirname(EMU_DIR), "..", "baseboostdepth_b200", "csrc")
+        deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc)]
+        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, src],
+                           check=True)
+        _EMU = _lib.Backend(so, "emu_", cuda=False)
+    return _EMU
+
+
+def run_fused(inputs, outputs, opt, noise, num_scales, backend=None, groups=None, want_winner=True):
+    s_rows = inputs[("color", "s", 0)].shape[0] if ("color", "s", 0) in inputs else None
+    plan = plan_for(inputs["ordering"], opt.trimin, opt.decomp, s_rows, groups)
+    losses = loss_step(inputs, outputs, opt, plan, noise=noise, num_scales=num_scales, backend=backend,
+                       want_winner=want_winner)
+    return losses, plan
+
+
+def to_device(d, device):
+    return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in d.items()}
