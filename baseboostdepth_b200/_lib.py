@@ -41,7 +41,8 @@ class ReprojArgs(C.Structure):
 class SmoothArgs(C.Structure):
     _fields_ = [("batch", C.c_int32), ("levels", C.c_int32), ("h", C.c_int32 * MAX_SCALES),
                 ("w", C.c_int32 * MAX_SCALES), ("disp", fp * MAX_SCALES), ("img", fp * MAX_SCALES),
-                ("gdisp", fp * MAX_SCALES), ("scratch", fp), ("loss", fp), ("max_chunks", C.c_int32)]
+                ("gdisp", fp * MAX_SCALES), ("scratch", fp), ("loss", fp), ("max_chunks", C.c_int32),
+                ("normalize", C.c_int32)]
 
 
 class D2DArgs(C.Structure):

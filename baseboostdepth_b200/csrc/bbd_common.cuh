@@ -31,6 +31,7 @@ BBD_HD float add(float a, float b) { return __fadd_rn(a, b); }
 BBD_HD float sub(float a, float b) { return __fsub_rn(a, b); }
 BBD_HD float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 BBD_HD float div_(float a, float b) { return __fdiv_rn(a, b); }
+BBD_HD float rcp_approx(float a) { return __fdividef(1.0f, a); }  // gradients only (<= 2 ulp)
 #else
 // host build is compiled with -ffp-contract=off
 BBD_HD float mul(float a, float b) { return a * b; }
@@ -38,7 +39,18 @@ BBD_HD float add(float a, float b) { return a + b; }
 BBD_HD float sub(float a, float b) { return a - b; }
 BBD_HD float fma_(float a, float b, float c) { return fmaf(a, b, c); }
 BBD_HD float div_(float a, float b) { return a / b; }
+BBD_HD float rcp_approx(float a) { return 1.0f / a; }
 #endif
+
+// a / d for a fixed divisor d with y = RN(1/d): q = RN(a*y); r = a - d*q (exact, FMA);
+// RN(q + r*y) is the correctly rounded quotient (Markstein).  Three instructions instead of
+// the IEEE division subroutine; equality with a / d is checked exhaustively over all 2^23
+// significands for the divisors used here (9, W-1, H-1) in tests/test_division.py.
+BBD_HD float div_const(float a, float d, float y) {
+  const float q = mul(a, y);
+  const float r = fma_(-d, q, a);
+  return fma_(r, y, q);
+}
 
 // SSIM constants (layers.py:232-233), photometric mix (trainer.py:485)
 #define BBD_C1 0.0001f
@@ -62,12 +74,17 @@ BBD_HD int reflect1(int i, int n) {
 struct Cam {
   float ik[9];
   float p[12];
+  float wm1, hm1, rw, rh;  // W-1, H-1 and their correctly rounded reciprocals
 };
 
-BBD_HD void load_cam(Cam& c, const float* inv_K4x4, const float* P3x4) {
+BBD_HD void load_cam(Cam& c, const float* inv_K4x4, const float* P3x4, int W, int H) {
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) c.ik[i * 3 + j] = inv_K4x4[i * 4 + j];
   for (int i = 0; i < 12; ++i) c.p[i] = P3x4[i];
+  c.wm1 = (float)(W - 1);
+  c.hm1 = (float)(H - 1);
+  c.rw = div_(1.0f, c.wm1);
+  c.rh = div_(1.0f, c.hm1);
 }
 
 // Everything the bilinear tap needs, and (for the backward) the partials of it.
@@ -98,13 +115,13 @@ BBD_HD void project_pixel(const Cam& c, int px, int py, float depth, int W, int 
   s.ux = div_(cx, s.zz);
   s.uy = div_(cy, s.zz);
   // pix /= (W-1); (pix - 0.5) * 2   (layers.py:191-193)
-  const float gx = mul(sub(div_(s.ux, (float)(W - 1)), 0.5f), 2.0f);
-  const float gy = mul(sub(div_(s.uy, (float)(H - 1)), 0.5f), 2.0f);
+  const float gx = mul(sub(div_const(s.ux, c.wm1, c.rw), 0.5f), 2.0f);
+  const float gy = mul(sub(div_const(s.uy, c.hm1, c.rh), 0.5f), 2.0f);
   // grid_sampler_unnormalize(align_corners): ((g + 1) / 2) * (size - 1)
-  float ix = mul(mul(add(gx, 1.0f), 0.5f), (float)(W - 1));
-  float iy = mul(mul(add(gy, 1.0f), 0.5f), (float)(H - 1));
+  float ix = mul(mul(add(gx, 1.0f), 0.5f), c.wm1);
+  float iy = mul(mul(add(gy, 1.0f), 0.5f), c.hm1);
   // clip_coordinates_set_grad: the border itself counts as outside for the gradient
-  const float wmax = (float)(W - 1), hmax = (float)(H - 1);
+  const float wmax = c.wm1, hmax = c.hm1;
   if (!(ix > 0.0f)) { ix = 0.0f; s.mx = 0.0f; } else if (ix >= wmax) { ix = wmax; s.mx = 0.0f; } else { s.mx = 1.0f; }
   if (!(iy > 0.0f)) { iy = 0.0f; s.my = 0.0f; } else if (iy >= hmax) { iy = hmax; s.my = 0.0f; } else { s.my = 1.0f; }
   s.ix = ix;
@@ -166,7 +183,7 @@ BBD_HD void tap_channel_grad(const float* plane, const Sample& s, const Taps& t,
 // (times the clip mask).  ux = cx / zz, uy = cy / zz.
 BBD_HD void chain_to_depth_pose(const Cam& c, const Sample& s, float gix, float giy, float& gdepth, float gP[12]) {
   const float gux = gix * s.mx, guy = giy * s.my;
-  const float inv = 1.0f / s.zz;
+  const float inv = rcp_approx(s.zz);
   const float gcx = gux * inv, gcy = guy * inv;
   const float gcz = -(gux * s.ux + guy * s.uy) * inv;
   gP[0] += gcx * s.X; gP[1] += gcx * s.Y; gP[2] += gcx * s.Z; gP[3] += gcx;
@@ -187,7 +204,7 @@ struct WinY {  // per-channel target statistics: mean and variance term
   float mu, sig;
 };
 
-BBD_HD float ninth(float s) { return div_(s, 9.0f); }
+BBD_HD float ninth(float s) { return div_const(s, 9.0f, 0.111111111938953399658203125f); }
 
 BBD_HD WinY target_stats(float sy, float syy) {
   WinY w;
@@ -220,7 +237,7 @@ BBD_HD float ssim_channel(const WinX& wx, const WinY& wy, SsimParts& q) {
 BBD_HD void ssim_coefs(const SsimParts& q, const WinY& wy, float g, float& a, float& b, float& c) {
   if (!(q.raw >= 0.0f && q.raw <= 1.0f)) { a = b = c = 0.0f; return; }
   const float gr = -0.5f * g;                  // raw = (1 - r)/2
-  const float invd = 1.0f / (q.d1 * q.d2);
+  const float invd = rcp_approx(q.d1 * q.d2);
   const float r_n = invd;                      // dr/dn
   const float r_d = -q.r * invd;               // dr/dd
   const float r_sigxy = r_n * q.n1 * 2.0f;
@@ -237,7 +254,7 @@ BBD_HD void ssim_coefs(const SsimParts& q, const WinY& wy, float g, float& a, fl
 BBD_HD void ssim_coefs_y(const SsimParts& q, const WinY& wy, float g, float& a, float& b, float& c) {
   if (!(q.raw >= 0.0f && q.raw <= 1.0f)) { a = b = c = 0.0f; return; }
   const float gr = -0.5f * g;
-  const float invd = 1.0f / (q.d1 * q.d2);
+  const float invd = rcp_approx(q.d1 * q.d2);
   const float r_n = invd, r_d = -q.r * invd;
   const float r_sigxy = r_n * q.n1 * 2.0f;
   const float r_sigy = r_d * q.d1;

@@ -123,19 +123,27 @@ __global__ void __launch_bounds__(128) reproj_finalize_kernel(const bbd_reproj_a
     return;
   }
   if (!gpose) return;
-  // one block per (scale, pose row): find the (sample, candidate) that uses this pose
+  // one block per (scale, pose row): find the (sample, candidate) that uses this pose, then
+  // 10 tile-lanes x 12 components sum the tile partials; a fixed-order tail adds the lanes.
   const int idx = blockIdx.x - S, s = idx / a.num_pose, pose = idx % a.num_pose;
-  float acc = 0.0f;  // thread tid<12 accumulates component tid
+  const int comp = tid % 12, lane = tid / 12;  // lanes 0..9 (tid < 120)
+  float acc = 0.0f;
   for (int b = 0; b < a.batch; ++b) {
     const int n_rep = a.tab.hdr[(size_t)b * 4];
     for (int k = 0; k < n_rep; ++k) {
       if (a.tab.rep[((size_t)b * BBD_MAX_REP + k) * 4 + 2] != pose) continue;
       const float* p = a.gpose_part + (((size_t)s * a.batch + b) * BBD_MAX_REP + k) * ntiles * 12;
-      if (tid < 12)
-        for (int tI = 0; tI < ntiles; ++tI) acc += p[(size_t)tI * 12 + tid];
+      if (tid < 120)
+        for (int tI = lane; tI < ntiles; tI += 10) acc += p[(size_t)tI * 12 + comp];
     }
   }
-  if (tid < 12) gpose[((size_t)s * a.num_pose + pose) * 12 + tid] = acc;
+  red[tid] = acc;
+  __syncthreads();
+  if (tid < 12) {
+    float tot = 0.0f;
+    for (int l = 0; l < 10; ++l) tot += red[l * 12 + tid];
+    gpose[((size_t)s * a.num_pose + pose) * 12 + tid] = tot;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -391,7 +399,8 @@ int bbd_disp_to_depth_backward(const bbd_d2d_args* a, bbd_stream_t stream) {
   size_t most = 1;
   for (int l = 0; l < a->levels; ++l) {
     if (!a->gdisp[l]) return fail(BBD_E_ARG, "d2d backward: bad level");
-    if (a->height % a->h[l] || a->width % a->w[l]) return fail(BBD_E_RANGE, "d2d backward: non-integer scale factor");
+    if (a->height % a->h[l] || a->width % a->w[l] || a->height / a->h[l] > 8 || a->width / a->w[l] > 8)
+      return fail(BBD_E_RANGE, "d2d backward: scale factor must be an integer <= 8");
     const size_t n = (size_t)a->batch * a->h[l] * a->w[l];
     if (n > most) most = n;
   }

@@ -39,36 +39,49 @@ BBD_HD float d2d_forward_px(const bbd_d2d_args& a, int lvl, int b, int oy, int o
   return div_(1.0f, add(a.min_disp, mul(a.disp_span, up)));
 }
 
-// one low-resolution disparity pixel: gather d(loss)/d(disp) from the full-res pixels it fed
+// one low-resolution disparity pixel: gather d(loss)/d(disp) from the full-res pixels it fed.
+// For an integer factor f the pixel (iy, ix) is a tap of the outputs in [f*i - f, f*i + 2f);
+// the weight of output o for input i is l0 if i0 == i plus l1 if i1 == i (both can hold at the
+// clamped borders), exactly the transpose of d2d_up.
+BBD_HD float d2d_axis_weight(int o, int i, int in_size, int out_size) {
+  const Lerp t = up_taps(o, in_size, out_size);
+  return (t.i0 == i ? t.l0 : 0.0f) + (t.i1 == i ? t.l1 : 0.0f);
+}
+
 BBD_HD float d2d_backward_px(const bbd_d2d_args& a, int lvl, int b, int iy, int ix) {
   const int h = a.h[lvl], w = a.w[lvl], H = a.height, W = a.width;
   const float* gd = a.gdepth + ((size_t)lvl * a.batch + b) * H * W;
   const float* dep = a.depth + ((size_t)lvl * a.batch + b) * H * W;
   const float span = a.disp_span;
-  const int fy = H / h, fx = W / w;
-  // outputs whose source coordinate lies within one input pixel of (iy, ix)
-  int oy_lo = iy * fy - fy, oy_hi = iy * fy + 2 * fy;
-  int ox_lo = ix * fx - fx, ox_hi = ix * fx + 2 * fx;
-  if (oy_lo < 0) oy_lo = 0;
-  if (ox_lo < 0) ox_lo = 0;
-  if (oy_hi > H) oy_hi = H;
-  if (ox_hi > W) ox_hi = W;
-  float acc = 0.0f;
-  for (int oy = oy_lo; oy < oy_hi; ++oy) {
-    const Lerp ty = up_taps(oy, h, H);
-    const float wy = (ty.i0 == iy ? ty.l0 : 0.0f) + (ty.i1 == iy ? ty.l1 : 0.0f);
-    if (wy == 0.0f) continue;
-    float row = 0.0f;
-    for (int ox = ox_lo; ox < ox_hi; ++ox) {
-      const Lerp tx = up_taps(ox, w, W);
-      const float wx = (tx.i0 == ix ? tx.l0 : 0.0f) + (tx.i1 == ix ? tx.l1 : 0.0f);
-      if (wx == 0.0f) continue;
-      const size_t o = (size_t)oy * W + ox;
-      float g = gd[o];
-      if (!a.sql) g *= -span * dep[o] * dep[o];
-      row += wx * g;
+  float acc;
+  if (h == H && w == W) {  // same resolution: the interpolation is the identity
+    const size_t o = (size_t)iy * W + ix;
+    acc = gd[o];
+    if (!a.sql) acc *= -span * dep[o] * dep[o];
+  } else {
+    const int fy = H / h, fx = W / w;
+    int oy_lo = iy * fy - fy, oy_hi = iy * fy + 2 * fy;
+    int ox_lo = ix * fx - fx, ox_hi = ix * fx + 2 * fx;
+    if (oy_lo < 0) oy_lo = 0;
+    if (ox_lo < 0) ox_lo = 0;
+    if (oy_hi > H) oy_hi = H;
+    if (ox_hi > W) ox_hi = W;
+    float wxs[24];  // factor <= 8
+    const int nx = ox_hi - ox_lo;
+    for (int k = 0; k < 24; ++k) wxs[k] = (k < nx) ? d2d_axis_weight(ox_lo + k, ix, w, W) : 0.0f;
+    acc = 0.0f;
+    for (int oy = oy_lo; oy < oy_hi; ++oy) {
+      const float wy = d2d_axis_weight(oy, iy, h, H);
+      if (wy == 0.0f) continue;
+      float row = 0.0f;
+      for (int k = 0; k < nx; ++k) {
+        const size_t o = (size_t)oy * W + ox_lo + k;
+        float g = gd[o];
+        if (!a.sql) g *= -span * dep[o] * dep[o];
+        row += wxs[k] * g;
+      }
+      acc += wy * row;
     }
-    acc += wy * row;
   }
   acc *= a.gscale[lvl];
   if (a.gsmooth[lvl]) acc += a.gsmooth_scale[lvl] * a.gsmooth[lvl][((size_t)b * h + iy) * w + ix];
@@ -79,7 +92,7 @@ BBD_HD float d2d_backward_px(const bbd_d2d_args& a, int lvl, int b, int iy, int 
 BBD_HD void warp_px(int H, int W, const float* images, const float* depth, const float* inv_K, const float* P,
                     int n, int py, int px, float* warped, float* grid) {
   Cam cam;
-  load_cam(cam, inv_K + (size_t)n * 16, P + (size_t)n * 12);
+  load_cam(cam, inv_K + (size_t)n * 16, P + (size_t)n * 12, W, H);
   Sample s;
   const size_t o = (size_t)py * W + px;
   project_pixel(cam, px, py, depth[(size_t)n * H * W + o], W, H, s);

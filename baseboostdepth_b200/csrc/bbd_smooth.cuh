@@ -68,7 +68,7 @@ BBD_HD void sm_stage2_thread(const SmoothArgs& a, int lvl, int b, int chunk, int
   const float* d = a.disp[lvl] + (size_t)b * n;
   const float* img = a.img[lvl] + (size_t)b * 3 * n;
   float* g = a.gdisp[lvl] ? a.gdisp[lvl] + (size_t)b * n : nullptr;
-  const float den = add(mean, 1e-7f);
+  const float den = a.normalize ? add(mean, 1e-7f) : 1.0f;
   const float inx = 1.0f / ((float)a.batch * (float)h * (float)(w - 1));
   const float iny = 1.0f / ((float)a.batch * (float)(h - 1) * (float)w);
   float stx = 0.0f, sty = 0.0f, sgd = 0.0f;
@@ -110,6 +110,7 @@ BBD_HD void sm_stage3_thread(const SmoothArgs& a, int lvl, int b, int chunk, int
   if (!a.gdisp[lvl]) return;
   const int n = a.h[lvl] * a.w[lvl];
   float* g = a.gdisp[lvl] + (size_t)b * n;
+  if (!a.normalize) return;  // g_d already is the gradient
   const float den = add(mean, 1e-7f);
   const float* p = sm_slot(a, lvl, b, 3);
   const int nc = sm_chunks(a.h[lvl], a.w[lvl]);

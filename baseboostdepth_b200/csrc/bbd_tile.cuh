@@ -159,7 +159,7 @@ BBD_HD void rp_target_stats(const bbd_reproj_args& a, ReprojSmem<C>& sm, const T
 BBD_HD void rp_candidate(const bbd_reproj_args& a, int b, int k, const float*& src, Cam& cam) {
   const int32_t* e = a.tab.rep + ((size_t)b * BBD_MAX_REP + k) * 4;
   src = a.frames[e[0]] + (size_t)e[1] * 3 * a.height * a.width;
-  load_cam(cam, a.inv_K + (size_t)e[3] * 16, a.P + (size_t)e[2] * 12);
+  load_cam(cam, a.inv_K + (size_t)e[3] * 16, a.P + (size_t)e[2] * 12, a.width, a.height);
 }
 
 template <class C>

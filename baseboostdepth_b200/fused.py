@@ -138,7 +138,7 @@ class _FusedLoss(torch.autograd.Function):
 
         # 5. smoothness on the disparity pyramid
         sa = _lib.SmoothArgs()
-        sa.batch, sa.levels = B, S
+        sa.batch, sa.levels, sa.normalize = B, S, 1
         gsm = []
         smooth_src = disps_c
         for l, d in enumerate(smooth_src):

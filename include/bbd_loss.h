@@ -133,6 +133,8 @@ typedef struct bbd_smooth_args {
   float* scratch;                    /* bbd_smooth_scratch_floats() floats */
   float* loss;                       /* (levels) */
   int32_t max_chunks;                /* set by the library */
+  int32_t normalize;                 /* 1: divide by the per-sample mean first (trainer.py:560-562);
+                                        0: plain get_smooth_loss(disp, img) (layers.py:203-216) */
 } bbd_smooth_args;
 size_t bbd_smooth_scratch_floats(int32_t batch, int32_t levels, const int32_t* h, const int32_t* w);
 int bbd_smooth_fused(const bbd_smooth_args* a, bbd_stream_t stream);

@@ -22,6 +22,21 @@ using Cfg = TileCfg<32, 16, 256>;
 
 extern "C" {
 
+// number of significands (all 2^23, three binades) for which div_const(a, d, RN(1/d)) != a / d
+long emu_div_const_mismatches(float d) {
+  const float y = 1.0f / d;
+  long bad = 0;
+  const uint32_t exps[3] = {100u, 127u, 140u};
+  for (int e = 0; e < 3; ++e)
+    for (uint32_t m = 0; m < (1u << 23); ++m) {
+      const uint32_t bits = (exps[e] << 23) | m;
+      float a;
+      memcpy(&a, &bits, 4);
+      if (div_const(a, d, y) != a / d) ++bad;
+    }
+  return bad;
+}
+
 int emu_reproj_tiles(int32_t height, int32_t width) {
   return ((width + Cfg::TW - 1) / Cfg::TW) * ((height + Cfg::TH - 1) / Cfg::TH);
 }

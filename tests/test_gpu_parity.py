@@ -10,7 +10,7 @@ import torch
 from baseboostdepth_b200.synthetic import make_batch, make_noise
 from baseboostdepth_b200.trainer import materialise_warps, plan_for
 from fused_util import run_fused, to_device
-from helpers import Golden, golden_cases, max_abs, rel_l2
+from helpers import Golden, assert_grad_parity, golden_cases, max_abs, pixel_agreement, rel_l2
 from oracle import loss_path as O
 
 pytestmark = pytest.mark.gpu
@@ -38,6 +38,9 @@ def test_golden_case_on_gpu(case, cuda_device):
     g = Golden(case)
     ref, aux = O.run(g.inputs, g.outputs, g.opt(), g.noise, num_scales=g.num_scales)
     ref["loss"].backward()
+    g64 = Golden(case, dtype=torch.float64)
+    ref64, _ = O.run(g64.inputs, g64.outputs, g64.opt(), g64.noise, num_scales=g.num_scales)
+    ref64["loss"].backward()
 
     h = Golden(case, device=cuda_device)
     noise = {k: v.to(cuda_device) for k, v in h.noise.items()}
@@ -49,8 +52,7 @@ def test_golden_case_on_gpu(case, cuda_device):
     for k, p in g.params.items():
         if p.grad is None:
             continue
-        r = rel_l2(h.params[k].grad, p.grad)
-        assert r <= 1e-5, (k, r)
+        assert_grad_parity(h.params[k].grad, p.grad, g64.params[k].grad, k)
     _selection_check(h.outputs["argmin"], plan, aux, h.scales)
     with torch.no_grad():
         materialise_warps(h.inputs, h.outputs, h.opt(), plan)
@@ -82,6 +84,9 @@ def test_full_size_against_oracle(name, cfg, cuda_device):
     noise = make_noise(plan, cfg["height"], cfg["width"], seed=5)
     ref, aux = O.run(inputs, outputs, opt, noise, num_scales=4)
     ref["loss"].backward()
+    i64, o64, p64 = make_batch(seed=21, device="cpu", dtype=torch.float64, scales=scales, **cfg)
+    ref64, _ = O.run(i64, o64, opt, {k: v.double() for k, v in noise.items()}, num_scales=4)
+    ref64["loss"].backward()
 
     gi, go, gp = make_batch(seed=21, device=cuda_device, scales=scales, **cfg)
     gnoise = {k: v.to(cuda_device) for k, v in noise.items()}
@@ -93,8 +98,10 @@ def test_full_size_against_oracle(name, cfg, cuda_device):
     for k, p in params.items():
         if p.grad is None:
             continue
-        r = rel_l2(gp[k].grad, p.grad)
-        assert r <= 1e-5, (k, r)
+        assert_grad_parity(gp[k].grad, p.grad, p64[k].grad, k)
+        if k[0] == "disp":   # per-pixel: all but the footprints of a few near-ties agree to 1e-4 of the peak
+            frac = pixel_agreement(gp[k].grad, p.grad, tol=1e-4)
+            assert frac <= 5e-3, (k, frac)
     _selection_check(go["argmin"], plan, aux, scales)
 
 

@@ -1,0 +1,171 @@
+"""Tier-A operators (drop-in ``layers`` module) against the oracle, kernels stepped on the CPU."""
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+import baseboostdepth_b200.layers as L
+from fused_util import emu_backend
+from helpers import Golden, max_abs, rel_l2
+from oracle import loss_path as O
+
+
+@pytest.fixture(autouse=True)
+def use_emulator():
+    L._TEST_BACKEND = emu_backend()
+    yield
+    L._TEST_BACKEND = None
+
+
+def _geometry(n=3, H=24, W=40, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    K = torch.tensor([[0.58 * W, 0, 0.5 * W, 0], [0, 1.92 * H, 0.5 * H, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
+    K = K.unsqueeze(0).repeat(n + 1, 1, 1)
+    inv_K = torch.linalg.pinv(K)
+    aa = 0.02 * torch.randn(n, 1, 3, generator=g)
+    tr = 0.05 * torch.randn(n, 1, 3, generator=g)
+    depth = (1.0 + 5.0 * torch.rand(n, 1, H, W, generator=g))
+    return K, inv_K, aa, tr, depth
+
+
+def test_backproject_project_forward_backward():
+    n, H, W = 3, 24, 40
+    K, inv_K, aa, tr, depth = _geometry(n, H, W)
+    outs = []
+    for mine in (False, True):
+        d = depth.clone().requires_grad_(True)
+        a, t = aa.clone().requires_grad_(True), tr.clone().requires_grad_(True)
+        T = L.transformation_from_parameters(a, t)
+        if mine:
+            bp, pj = L.BackprojectDepth(n + 1, H, W), L.Project3D(n + 1, H, W)   # batch_size > n: sub-batch
+            cam = bp(d, inv_K[:n])
+            pix = pj(cam, K[:n], T)
+        else:
+            cam = O.backproject(d, inv_K[:n], H, W)
+            pix = O.project(cam, K[:n], T, H, W)
+        w = torch.linspace(0.5, 1.5, pix.numel()).view_as(pix)
+        (pix * w).sum().backward()
+        outs.append((cam.detach(), pix.detach(), d.grad, a.grad, t.grad))
+    ref, got = outs
+    assert got[1].shape == ref[1].shape and got[1].stride() == ref[1].stride()   # same non-contiguous view
+    assert max_abs(got[0], ref[0]) == 0.0
+    assert max_abs(got[1], ref[1]) <= 1e-6
+    for i in (2, 3, 4):
+        assert rel_l2(got[i], ref[i]) <= 1e-5, i
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 16, 20), (1, 1, 2, 5), (2, 2, 9, 3)])
+def test_ssim_forward_backward(shape):
+    g = torch.Generator().manual_seed(1)
+    x0, y0 = torch.rand(*shape, generator=g), torch.rand(*shape, generator=g)
+    w = torch.rand(*shape, generator=g)
+    res = []
+    for mine in (False, True):
+        x, y = x0.clone().requires_grad_(True), y0.clone().requires_grad_(True)
+        out = L.SSIM()(x, y) if mine else O.ssim(x, y)
+        (out * w).sum().backward()
+        res.append((out.detach(), x.grad, y.grad))
+    assert max_abs(res[1][0], res[0][0]) <= 1e-6
+    assert rel_l2(res[1][1], res[0][1]) <= 2e-5
+    assert rel_l2(res[1][2], res[0][2]) <= 2e-5
+
+
+def test_ssim_accepts_non_contiguous():
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(2, 8, 10, 3, generator=g).permute(0, 3, 1, 2)
+    y = torch.rand(2, 3, 8, 10, generator=g)
+    assert max_abs(L.SSIM()(x, y), O.ssim(x, y)) <= 1e-6
+
+
+def test_smooth_loss_forward_backward():
+    g = torch.Generator().manual_seed(3)
+    img = torch.rand(3, 3, 12, 50, generator=g)
+    d0 = torch.rand(3, 1, 12, 50, generator=g)
+    res = []
+    for mine in (False, True):
+        d = d0.clone().requires_grad_(True)
+        norm = d / (d.mean(2, True).mean(3, True) + 1e-7)      # as the trainer does (trainer.py:560-562)
+        loss = (L.get_smooth_loss if mine else O.smooth_loss)(norm, img)
+        (2.5 * loss).backward()
+        res.append((loss.detach(), d.grad))
+    assert abs(float(res[1][0]) - float(res[0][0])) <= 1e-6
+    assert rel_l2(res[1][1], res[0][1]) <= 1e-5
+
+
+def test_module_surface():
+    names = ["SSIM", "BackprojectDepth", "Project3D", "transformation_from_parameters", "disp_to_depth",
+             "get_smooth_loss", "compute_depth_errors", "ConvBlock", "Conv3x3", "upsample", "rot_from_axisangle",
+             "get_translation_matrix"]
+    for n in names:
+        assert hasattr(L, n), n
+    assert len(list(L.BackprojectDepth(2, 8, 8).state_dict())) == 0      # stateless; never checkpointed
+    assert len(list(L.Project3D(2, 8, 8).state_dict())) == 0
+    L.SSIM().to("cpu")
+
+
+def test_geometry_helpers_bit_identical():
+    g = torch.Generator().manual_seed(4)
+    aa, tr = 0.3 * torch.randn(5, 1, 3, generator=g), torch.randn(5, 1, 3, generator=g)
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("reference not mounted (GPU box)")
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, "/root/reference")
+    try:
+        import importlib
+        ref = importlib.import_module("layers")
+    finally:
+        sys.path.remove("/root/reference")
+    for inv in (False, True):
+        assert torch.equal(L.transformation_from_parameters(aa, tr, inv), ref.transformation_from_parameters(aa, tr, inv))
+    d = torch.rand(2, 1, 4, 4, generator=g)
+    assert torch.equal(L.disp_to_depth(d, 0.1, 100)[1], ref.disp_to_depth(d, 0.1, 100)[1])
+
+
+def test_reference_trainer_runs_unchanged_on_drop_in_layers():
+    """Tier A end to end: the reference's own Trainer methods, with this package's layers swapped in."""
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("reference not mounted (GPU box)")
+    for name in ("skimage", "skimage.transform", "matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib.pyplot"].get_cmap = lambda *a, **k: None
+    sys.dont_write_bytecode = True
+    threads = torch.get_num_threads()
+    saved_layers = sys.modules.pop("layers", None)
+    sys.modules["layers"] = L                      # `from layers import ...` now resolves to the drop-in
+    sys.modules.pop("trainer", None)
+    sys.path.insert(0, "/root/reference")
+    try:
+        import trainer as ref_trainer
+    finally:
+        sys.path.remove("/root/reference")
+        torch.set_num_threads(threads)
+    try:
+        g = Golden("plain_pm1")
+        tr = ref_trainer.Trainer.__new__(ref_trainer.Trainer)
+        tr.opt = types.SimpleNamespace(**vars(g.opt()))
+        tr.device, tr.num_scales, tr.maxing_valid_frames = torch.device("cpu"), g.num_scales, False
+        B = len(g.baselines)
+        tr.ssim = L.SSIM()
+        tr.backproject_depth = {0: L.BackprojectDepth(B, g.H, g.W)}
+        tr.project_3d = {0: L.Project3D(B, g.H, g.W)}
+        tr.opt.frame_ids = O.frame_ids_from_ordering(g.ordering)
+        tr.valid_frames = O.initial_valid_frames(g.ordering)
+        tr.valid_frames_trimin(g.inputs)
+        real_randn, drawn = torch.randn, iter([g.noise[k] / 0.00001 for k in [f for f in tr.valid_frames if f == "s" or f > 0]])
+        torch.randn = lambda *a, **k: next(drawn)
+        try:
+            tr.generate_images_pred(g.inputs, g.outputs)
+            losses = tr.compute_losses(g.inputs, g.outputs)
+        finally:
+            torch.randn = real_randn
+        assert abs(float(losses["loss"]) - g.losses["loss"]) <= 2e-6
+        losses["loss"].backward()
+        for k, ref in g.grads.items():
+            assert rel_l2(g.params[k].grad, ref) <= 2e-5, k
+    finally:
+        sys.modules.pop("trainer", None)
+        sys.modules.pop("layers", None)
+        if saved_layers is not None:
+            sys.modules["layers"] = saved_layers
