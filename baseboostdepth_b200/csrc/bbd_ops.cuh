@@ -13,21 +13,25 @@ struct Lerp {
   float l0, l1;
 };
 BBD_HD Lerp up_taps(int o, int in_size, int out_size) {
-  const float scale = (float)in_size / (float)out_size;
-  float src = scale * ((float)o + 0.5f) - 0.5f;
+  const float scale = div_((float)in_size, (float)out_size);
+  float src = sub(mul(scale, add((float)o, 0.5f)), 0.5f);
   if (src < 0.0f) src = 0.0f;
   Lerp t;
   t.i0 = (int)src;
   t.i1 = t.i0 + ((t.i0 < in_size - 1) ? 1 : 0);
-  t.l1 = src - (float)t.i0;
-  t.l0 = 1.0f - t.l1;
+  t.l1 = sub(src, (float)t.i0);
+  t.l0 = sub(1.0f, t.l1);
   return t;
 }
 
 BBD_HD float d2d_up(const float* d, int w, const Lerp& ty, const Lerp& tx) {
   const float* r0 = d + (size_t)ty.i0 * w;
   const float* r1 = d + (size_t)ty.i1 * w;
-  return ty.l0 * (tx.l0 * r0[tx.i0] + tx.l1 * r0[tx.i1]) + ty.l1 * (tx.l0 * r1[tx.i0] + tx.l1 * r1[tx.i1]);
+  // rounding pattern of ATen's upsample_bilinear2d (checked bit-for-bit against torch CPU):
+  // each lerp is fma(w0, a, RN(w1 * b))
+  const float top = fma_(tx.l0, r0[tx.i0], mul(tx.l1, r0[tx.i1]));
+  const float bot = fma_(tx.l0, r1[tx.i0], mul(tx.l1, r1[tx.i1]));
+  return fma_(ty.l0, top, mul(ty.l1, bot));
 }
 
 // one full-resolution pixel: upsample + disp_to_depth (layers.py:13-22)
