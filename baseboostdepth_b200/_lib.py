@@ -59,7 +59,7 @@ EXPORTS = [
     "bbd_reproj_finalize", "bbd_warp_forward", "bbd_smooth_scratch_floats", "bbd_smooth_fused",
     "bbd_disp_to_depth_forward", "bbd_disp_to_depth_backward", "bbd_backproject_forward",
     "bbd_backproject_backward", "bbd_project_forward", "bbd_project_chunks", "bbd_project_backward",
-    "bbd_ssim_forward", "bbd_ssim_backward",
+    "bbd_ssim_forward", "bbd_ssim_backward", "bbd_pose_pack_forward", "bbd_pose_pack_backward",
 ]
 
 

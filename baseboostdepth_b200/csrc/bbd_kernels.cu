@@ -8,13 +8,16 @@
 
 #include "bbd_ops.cuh"
 #include "bbd_smooth.cuh"
+#include "bbd_strip.cuh"
 #include "bbd_tile.cuh"
 
 namespace bbd {
 
-// Tile shape of the fused loss: 32x16 target pixels per block of 256 threads.  With two
-// warped candidates the block needs ~83 KB of shared memory -> 2 blocks per SM.
+// Identity pre-pass: 32x16 target pixels per block of 256 threads.
 using Cfg = TileCfg<32, 16, 256>;
+// Fused loss: 28x20 target pixels per block of 8 warps, lanes = columns (bbd_strip.cuh).  With two
+// warped candidates the block needs ~91 KB of shared memory -> 2 blocks per SM.
+using SCfg = StripCfg<20, 8>;
 
 static thread_local char g_err[256] = "";
 
@@ -61,28 +64,28 @@ __global__ void __launch_bounds__(Cfg::NT) ident_kernel(const bbd_ident_args a) 
 // fused reprojection loss
 // ------------------------------------------------------------------------------------------
 template <bool GRAD>
-__global__ void __launch_bounds__(Cfg::NT) reproj_kernel(const bbd_reproj_args a) {
+__global__ void __launch_bounds__(SCfg::NT, 2) reproj_kernel(const bbd_reproj_args a) {
   extern __shared__ float smem[];
-  ReprojSmem<Cfg> sm;
+  StripSmem<SCfg> sm;
   sm.carve(smem, a.max_rep);
   const int tid = threadIdx.x;
-  TileId t = make_tile(blockIdx.x, blockIdx.y, blockIdx.z, a.batch, a.height, a.width, Cfg::TW, Cfg::TH);
+  const StripCtx t = make_strip<SCfg>(blockIdx.x, blockIdx.y, blockIdx.z, tid, a.batch, a.height, a.width);
   const int n_rep = a.tab.hdr[(size_t)t.b * 4];
 
-  rp_load_target<Cfg>(a, sm, t, tid);
+  rs_load_target<SCfg>(a, sm, t, tid);
   __syncthreads();
-  rp_target_stats<Cfg>(a, sm, t, tid);
+  rs_target_stats<SCfg>(a, sm, t);
   for (int k = 0; k < n_rep; ++k) {
-    rp_warp<Cfg>(a, sm, t, k, tid);
+    rs_warp<SCfg>(a, sm, t, k);
     __syncthreads();
-    rp_stats<Cfg>(a, sm, t, k, tid);
+    rs_stats<SCfg>(a, sm, t, k);
   }
-  const float part = rp_select<Cfg>(a, sm, t, n_rep, tid);
-  red_park<Cfg, 1>(sm.red, tid, &part);
+  const float part = rs_select<SCfg>(a, sm, t, n_rep);
+  rs_park<SCfg, 1>(sm.red, tid, &part);
   __syncthreads();
-  red_level1<Cfg, 1>(sm.red, tid);
+  rs_level1<SCfg, 1>(sm.red, tid);
   __syncthreads();
-  red_level2<Cfg, 1>(sm.red, tid, a.loss_part + ((size_t)t.s * a.batch + t.b) * t.ntiles + t.tile);
+  rs_level2<SCfg, 1>(sm.red, tid, a.loss_part + ((size_t)t.s * a.batch + t.b) * t.ntiles + t.tile);
 
   if (GRAD) {
     for (int k = 0; k < BBD_MAX_REP; ++k) {
@@ -92,14 +95,14 @@ __global__ void __launch_bounds__(Cfg::NT) reproj_kernel(const bbd_reproj_args a
         continue;
       }
       float gP[12];
-      rp_backward<Cfg>(a, sm, t, k, tid, gP);
-      red_park<Cfg, 12>(sm.red, tid, gP);
+      rs_backward<SCfg>(a, sm, t, k, gP);
+      rs_park<SCfg, 12>(sm.red, tid, gP);
       __syncthreads();
-      red_level1<Cfg, 12>(sm.red, tid);
+      rs_level1<SCfg, 12>(sm.red, tid);
       __syncthreads();
-      red_level2<Cfg, 12>(sm.red, tid, out);
+      rs_level2<SCfg, 12>(sm.red, tid, out);
     }
-    rp_store_gdepth<Cfg>(a, sm, t, tid);
+    rs_store_gdepth<SCfg>(a, sm, t);
   }
 }
 
@@ -229,6 +232,19 @@ __global__ void d2d_backward_kernel(const bbd_d2d_args a) {
   }
 }
 
+__global__ void pose_pack_kernel(int n, const float* K, const int32_t* k_row, const float* T, float* P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 12) return;
+  const int p = i / 12, e = i % 12;
+  P[i] = pose_pack_elem(K + (size_t)k_row[p] * 16, T + (size_t)p * 16, e / 4, e % 4);
+}
+__global__ void pose_pack_grad_kernel(int n, const float* K, const int32_t* k_row, const float* gP, float* gT) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 16) return;
+  const int p = i / 16, e = i % 16;
+  gT[i] = pose_pack_grad_elem(K + (size_t)k_row[p] * 16, gP + (size_t)p * 12, e / 4, e % 4);
+}
+
 __global__ void warp_kernel(int n, int H, int W, const float* images, const float* depth, const float* inv_K,
                             const float* P, float* warped, float* grid) {
   const size_t total = (size_t)n * H * W;
@@ -315,7 +331,7 @@ int bbd_version(void) { return BBD_ABI_VERSION; }
 const char* bbd_last_error_string(void) { return g_err; }
 
 int bbd_reproj_tiles(int32_t height, int32_t width) {
-  return ((width + Cfg::TW - 1) / Cfg::TW) * ((height + Cfg::TH - 1) / Cfg::TH);
+  return ((width + SCfg::TW - 1) / SCfg::TW) * ((height + SCfg::TH - 1) / SCfg::TH);
 }
 
 int bbd_ident_forward(const bbd_ident_args* a, bbd_stream_t stream) {
@@ -334,15 +350,15 @@ int bbd_reproj_fused(const bbd_reproj_args* a, bbd_stream_t stream) {
   if (a->need_grad && (!a->gpose_part || !a->gdepth)) return fail(BBD_E_ARG, "reproj: gradient buffers missing");
   if (a->batch <= 0 || a->height < 2 || a->width < 2 || a->num_scales <= 0) return fail(BBD_E_ARG, "reproj: bad size");
   if (a->max_rep < 1 || a->max_rep > BBD_MAX_REP) return fail(BBD_E_RANGE, "reproj: max_rep out of range");
-  const size_t smem = ReprojSmem<Cfg>::floats(a->max_rep) * sizeof(float);
+  const size_t smem = StripSmem<SCfg>::floats(a->max_rep) * sizeof(float);
   if (smem > 227 * 1024) return fail(BBD_E_RANGE, "reproj: shared memory budget exceeded");
-  dim3 grid((a->width + Cfg::TW - 1) / Cfg::TW, (a->height + Cfg::TH - 1) / Cfg::TH, a->num_scales * a->batch);
+  dim3 grid((a->width + SCfg::TW - 1) / SCfg::TW, (a->height + SCfg::TH - 1) / SCfg::TH, a->num_scales * a->batch);
   if (a->need_grad) {
     cudaFuncSetAttribute(reproj_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    reproj_kernel<true><<<grid, Cfg::NT, smem, (cudaStream_t)stream>>>(*a);
+    reproj_kernel<true><<<grid, SCfg::NT, smem, (cudaStream_t)stream>>>(*a);
   } else {
     cudaFuncSetAttribute(reproj_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    reproj_kernel<false><<<grid, Cfg::NT, smem, (cudaStream_t)stream>>>(*a);
+    reproj_kernel<false><<<grid, SCfg::NT, smem, (cudaStream_t)stream>>>(*a);
   }
   return check_launch("reproj_kernel");
 }
@@ -407,6 +423,22 @@ int bbd_disp_to_depth_backward(const bbd_d2d_args* a, bbd_stream_t stream) {
   dim3 grid(grid_for(most, 128), 1, a->levels);
   d2d_backward_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*a);
   return check_launch("d2d_backward_kernel");
+}
+
+int bbd_pose_pack_forward(int32_t n_pose, const float* K, const int32_t* k_row, const float* T, float* P,
+                          bbd_stream_t stream) {
+  if (!K || !k_row || !T || !P) return fail(BBD_E_ARG, "pose_pack: null argument");
+  if (n_pose <= 0) return 0;
+  pose_pack_kernel<<<(n_pose * 12 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_pose, K, k_row, T, P);
+  return check_launch("pose_pack_kernel");
+}
+
+int bbd_pose_pack_backward(int32_t n_pose, const float* K, const int32_t* k_row, const float* gP, float* gT,
+                           bbd_stream_t stream) {
+  if (!K || !k_row || !gP || !gT) return fail(BBD_E_ARG, "pose_pack backward: null argument");
+  if (n_pose <= 0) return 0;
+  pose_pack_grad_kernel<<<(n_pose * 16 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_pose, K, k_row, gP, gT);
+  return check_launch("pose_pack_grad_kernel");
 }
 
 int bbd_warp_forward(int32_t n, int32_t height, int32_t width, const float* images, const float* depth, const float* inv_K,

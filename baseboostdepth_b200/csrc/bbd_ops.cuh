@@ -92,6 +92,21 @@ BBD_HD float d2d_backward_px(const bbd_d2d_args& a, int lvl, int b, int iy, int 
   return acc;
 }
 
+// ---- P = (K @ T)[:3] (layers.py:182), one output element.  For these tiny batched 4x4 products
+// ATen's CPU bmm takes its naive loop (separately rounded multiply and add, k ascending) -- checked
+// bit-for-bit; the large (3x4)@(4xHW) products go through the FMA chain used in project_pixel.
+BBD_HD float pose_pack_elem(const float* K, const float* T, int i, int j) {
+  float acc = mul(K[i * 4], T[j]);
+  acc = add(acc, mul(K[i * 4 + 1], T[4 + j]));
+  acc = add(acc, mul(K[i * 4 + 2], T[8 + j]));
+  acc = add(acc, mul(K[i * 4 + 3], T[12 + j]));
+  return acc;
+}
+// gT[k][j] = sum_{i<3} K[i][k] * gP[i][j]
+BBD_HD float pose_pack_grad_elem(const float* K, const float* gP, int k, int j) {
+  return K[k] * gP[j] + K[4 + k] * gP[4 + j] + K[8 + k] * gP[8 + j];
+}
+
 // ---- on-demand warp (trainer.py:434-442): one output pixel, three channels ----------------
 BBD_HD void warp_px(int H, int W, const float* images, const float* depth, const float* inv_K, const float* P,
                     int n, int py, int px, float* warped, float* grid) {

@@ -1,0 +1,376 @@
+// Fused reprojection loss, tile phases v2: lanes are columns.
+//
+// A block of NW warps owns a tile of 28 x TH target pixels.  The 32 lanes of a warp map to
+// the 32 columns of the tile's +-2 halo region (28 interior + 4 halo), warps stride over rows.
+// Every shared-memory plane has a row pitch of 32 floats, so a warp always touches 32
+// consecutive words (conflict-free) and no division / modulo is needed to find a slot.
+// Work is organised in phases separated by block barriers exactly like bbd_tile.cuh, and the
+// phase bodies are __host__ __device__ so tests/emu can step them on the CPU.
+//
+// Regions (padded image coordinates; reflection resolved when a value is produced):
+//   R2: rows 0..TH+3, lanes 0..31   warped / target values        u = x0-2+lane, v = y0-2+row
+//   R1: rows 0..TH+1, lanes 1..30   window centres                (R1 row i = R2 row i+1)
+//   IN: rows 0..TH-1, lanes 2..29   pixels whose gradient we own  (IN row q = R2 row q+2)
+#pragma once
+#include "bbd_common.cuh"
+
+namespace bbd {
+
+template <int TH_, int NW_>
+struct StripCfg {
+  static constexpr int TW = 28, TH = TH_, NW = NW_, NT = NW_ * 32;
+  static constexpr int P = 32;  // row pitch (floats) of every shared plane
+  static constexpr int R2H = TH + 4, R1H = TH + 2;
+  static constexpr int R2N = R2H * P, R1N = R1H * P, INN = TH * P;
+  static constexpr int RED_SEG = 16;
+  static_assert(NT % RED_SEG == 0 && NT / RED_SEG <= RED_SEG * 2, "reduction shape");
+};
+
+template <class C>
+struct StripSmem {
+  float* tgt;    // [3][R2N]
+  float* pred;   // [max_rep][3][R2N]
+  float* tst;    // [6][R1N]
+  float* stash;  // [9][R1N]  window sums of the best candidate -> gradient coefficients
+  float* best;   // [R1N]
+  int* bidx;     // [R1N]
+  float* gd;     // [INN]
+  float* red;    // [12][NT] + [12][RED_SEG*2]
+  int* anywin;   // [BBD_MAX_REP]
+  static constexpr size_t floats(int max_rep) {
+    return 3 * C::R2N + (size_t)max_rep * 3 * C::R2N + 6 * C::R1N + 9 * C::R1N + 2 * C::R1N + C::INN + 12 * C::NT +
+           12 * C::RED_SEG * 2 + BBD_MAX_REP;
+  }
+  BBD_HD void carve(float* base, int max_rep) {
+    tgt = base; base += 3 * C::R2N;
+    pred = base; base += (size_t)max_rep * 3 * C::R2N;
+    tst = base; base += 6 * C::R1N;
+    stash = base; base += 9 * C::R1N;
+    best = base; base += C::R1N;
+    bidx = reinterpret_cast<int*>(base); base += C::R1N;
+    gd = base; base += C::INN;
+    red = base; base += 12 * C::NT + 12 * C::RED_SEG * 2;
+    anywin = reinterpret_cast<int*>(base);
+  }
+};
+
+// Per-thread constants of a tile.
+struct StripCtx {
+  int s, b, tile, ntiles;
+  int x0, y0;
+  int lane, warp;
+  int u;        // padded column of this lane
+  int px;       // reflected (real) column
+  bool col_in;  // padded column lies inside the image (a window centre / owned pixel can live here)
+};
+
+template <class C>
+BBD_HD StripCtx make_strip(int bx, int by, int bz, int tid, int batch, int H, int W) {
+  StripCtx t;
+  const int tiles_x = (W + C::TW - 1) / C::TW, tiles_y = (H + C::TH - 1) / C::TH;
+  t.s = bz / batch;
+  t.b = bz % batch;
+  t.x0 = bx * C::TW;
+  t.y0 = by * C::TH;
+  t.tile = by * tiles_x + bx;
+  t.ntiles = tiles_x * tiles_y;
+  t.lane = tid & 31;
+  t.warp = tid >> 5;
+  t.u = t.x0 - 2 + t.lane;
+  t.px = reflect1(t.u, W);
+  t.col_in = t.u >= 0 && t.u < W;
+  return t;
+}
+
+// 3x3 sums over a plane with pitch 32, top-left at p (row-major like ATen's avg_pool2d loop)
+BBD_HD float w9(const float* p) {
+  float s = p[0];
+  s = add(s, p[1]); s = add(s, p[2]);
+  s = add(s, p[32]); s = add(s, p[33]); s = add(s, p[34]);
+  s = add(s, p[64]); s = add(s, p[65]); s = add(s, p[66]);
+  return s;
+}
+BBD_HD float w9p(const float* p, const float* q) {
+  float s = mul(p[0], q[0]);
+  s = add(s, mul(p[1], q[1])); s = add(s, mul(p[2], q[2]));
+  s = add(s, mul(p[32], q[32])); s = add(s, mul(p[33], q[33])); s = add(s, mul(p[34], q[34]));
+  s = add(s, mul(p[64], q[64])); s = add(s, mul(p[65], q[65])); s = add(s, mul(p[66], q[66]));
+  return s;
+}
+
+template <class C>
+BBD_HD void rs_load_target(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t, int tid) {
+  const int H = a.height, W = a.width, HW = H * W;
+  const float* img = a.target + (size_t)t.b * 3 * HW;
+  for (int j = t.warp; j < C::R2H; j += C::NW) {
+    const int o = reflect1(t.y0 - 2 + j, H) * W + t.px;
+    const int i = j * C::P + t.lane;
+    sm.tgt[i] = img[o];
+    sm.tgt[C::R2N + i] = img[HW + o];
+    sm.tgt[2 * C::R2N + i] = img[2 * HW + o];
+  }
+  if (tid < BBD_MAX_REP) sm.anywin[tid] = 0;
+  for (int i = tid; i < C::INN; i += C::NT) sm.gd[i] = 0.0f;
+}
+
+// is R1 slot (row i, this lane) a window centre inside the image?
+template <class C>
+BBD_HD bool rs_center(const bbd_reproj_args& a, const StripCtx& t, int i, int& py) {
+  py = t.y0 - 1 + i;
+  return t.lane >= 1 && t.lane <= 30 && t.col_in && py >= 0 && py < a.height;
+}
+
+template <class C>
+BBD_HD void rs_target_stats(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t) {
+  if (a.no_ssim) return;
+  for (int i = t.warp; i < C::R1H; i += C::NW) {
+    int py;
+    if (!rs_center<C>(a, t, i, py)) continue;
+    const int o = i * C::P + t.lane - 1;  // top-left of the window in R2 coordinates
+    const int j = i * C::P + t.lane;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* y = sm.tgt + c * C::R2N + o;
+      const WinY w = target_stats(w9(y), w9p(y, y));
+      sm.tst[(2 * c) * C::R1N + j] = w.mu;
+      sm.tst[(2 * c + 1) * C::R1N + j] = w.sig;
+    }
+  }
+}
+
+BBD_HD void rs_candidate(const bbd_reproj_args& a, int b, int k, const float*& src, Cam& cam) {
+  const int32_t* e = a.tab.rep + ((size_t)b * BBD_MAX_REP + k) * 4;
+  src = a.frames[e[0]] + (size_t)e[1] * 3 * a.height * a.width;
+  load_cam(cam, a.inv_K + (size_t)e[3] * 16, a.P + (size_t)e[2] * 12, a.width, a.height);
+}
+
+template <class C>
+BBD_HD void rs_warp(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t, int k) {
+  const int H = a.height, W = a.width, HW = H * W;
+  const float* src;
+  Cam cam;
+  rs_candidate(a, t.b, k, src, cam);
+  const float* depth = a.depth + ((size_t)t.s * a.batch + t.b) * HW;
+  float* pred = sm.pred + (size_t)k * 3 * C::R2N;
+  for (int j = t.warp; j < C::R2H; j += C::NW) {
+    const int py = reflect1(t.y0 - 2 + j, H);
+    Sample s;
+    project_pixel(cam, t.px, py, depth[py * W + t.px], W, H, s);
+    Taps tp;
+    make_taps(s, W, H, tp);
+    const int i = j * C::P + t.lane;
+    pred[i] = tap_channel(src, tp);
+    pred[C::R2N + i] = tap_channel(src + HW, tp);
+    pred[2 * C::R2N + i] = tap_channel(src + 2 * HW, tp);
+  }
+}
+
+template <class C>
+BBD_HD void rs_stats(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t, int k) {
+  const float* pred = sm.pred + (size_t)k * 3 * C::R2N;
+  for (int i = t.warp; i < C::R1H; i += C::NW) {
+    int py;
+    if (!rs_center<C>(a, t, i, py)) continue;
+    const int o = i * C::P + t.lane - 1;
+    const int ctr = o + C::P + 1;
+    const int j = i * C::P + t.lane;
+    float ssim_sum = 0.0f, l1_sum = 0.0f;
+    WinX wx[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* x = pred + c * C::R2N;
+      const float* y = sm.tgt + c * C::R2N;
+      const float l1 = fabsf(sub(y[ctr], x[ctr]));
+      l1_sum = (c == 0) ? l1 : add(l1_sum, l1);
+      if (!a.no_ssim) {
+        wx[c].sx = w9(x + o);
+        wx[c].sxx = w9p(x + o, x + o);
+        wx[c].sxy = w9p(x + o, y + o);
+        WinY wy;
+        wy.mu = sm.tst[(2 * c) * C::R1N + j];
+        wy.sig = sm.tst[(2 * c + 1) * C::R1N + j];
+        SsimParts q;
+        const float v = ssim_channel(wx[c], wy, q);
+        ssim_sum = (c == 0) ? v : add(ssim_sum, v);
+      }
+    }
+    const float loss = photometric_mix(ssim_sum, l1_sum, a.no_ssim != 0);
+    if (k == 0 || loss < sm.best[j]) {
+      sm.best[j] = loss;
+      sm.bidx[j] = k;
+      if (!a.no_ssim) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          sm.stash[(3 * c) * C::R1N + j] = wx[c].sx;
+          sm.stash[(3 * c + 1) * C::R1N + j] = wx[c].sxx;
+          sm.stash[(3 * c + 2) * C::R1N + j] = wx[c].sxy;
+        }
+      }
+    }
+  }
+}
+
+// Winner against the identity minimum, loss partial, gradient coefficients of the winner.
+template <class C>
+BBD_HD float rs_select(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t, int n_rep) {
+  const int H = a.height, W = a.width;
+  const float wgt = 1.0f / ((float)a.batch * (float)H * (float)W);
+  const float g_ssim = wgt * BBD_W_SSIM * BBD_THIRD;
+  float part = 0.0f;
+  for (int i = t.warp; i < C::R1H; i += C::NW) {
+    int py;
+    const bool inside = rs_center<C>(a, t, i, py);
+    const int j = i * C::P + t.lane;
+    int win = -1;
+    if (inside) {
+      const size_t o = ((size_t)t.b * H + py) * W + t.px;
+      const float idm = a.ident_min[o];
+      const float bst = sm.best[j];
+      const bool rep_wins = bst <= idm;  // ties go to the lower index = the warped candidate
+      if (rep_wins) win = sm.bidx[j];
+      const bool interior = t.lane >= 2 && t.lane <= 29 && i >= 1 && i <= C::TH;
+      if (interior) {
+        part += rep_wins ? bst : idm;
+        if (a.winner)
+          a.winner[(((size_t)t.s * a.batch + t.b) * H + py) * W + t.px] =
+              (uint8_t)(rep_wins ? win : n_rep + (a.ident_arg ? a.ident_arg[o] : 0));
+      }
+    }
+    if (a.need_grad) {
+      if (win >= 0 && !a.no_ssim) {
+        sm.anywin[win] = 1;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          WinX wx;
+          wx.sx = sm.stash[(3 * c) * C::R1N + j];
+          wx.sxx = sm.stash[(3 * c + 1) * C::R1N + j];
+          wx.sxy = sm.stash[(3 * c + 2) * C::R1N + j];
+          WinY wy;
+          wy.mu = sm.tst[(2 * c) * C::R1N + j];
+          wy.sig = sm.tst[(2 * c + 1) * C::R1N + j];
+          SsimParts q;
+          ssim_channel(wx, wy, q);
+          float ca, cb, cc;
+          ssim_coefs(q, wy, g_ssim, ca, cb, cc);
+          sm.stash[(3 * c) * C::R1N + j] = ca;
+          sm.stash[(3 * c + 1) * C::R1N + j] = cb;
+          sm.stash[(3 * c + 2) * C::R1N + j] = cc;
+        }
+      } else {
+        if (win >= 0) sm.anywin[win] = 1;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) sm.stash[c * C::R1N + j] = 0.0f;
+      }
+    }
+    sm.bidx[j] = win;
+  }
+  return part;
+}
+
+template <class C>
+BBD_HD void rs_backward(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t, int k, float gP[12]) {
+  const int H = a.height, W = a.width, HW = H * W;
+  const float wgt = 1.0f / ((float)a.batch * (float)H * (float)W);
+  const float g_l1 = a.no_ssim ? wgt * BBD_THIRD : wgt * BBD_W_L1 * BBD_THIRD;
+  const float* src;
+  Cam cam;
+  rs_candidate(a, t.b, k, src, cam);
+  const float* depth = a.depth + ((size_t)t.s * a.batch + t.b) * HW;
+  const float* pred = sm.pred + (size_t)k * 3 * C::R2N;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) gP[i] = 0.0f;
+  const bool lane_ok = t.lane >= 2 && t.lane <= 29 && t.u < W;
+  // multiplicity of a neighbouring window: a reflected border pixel sits twice in it
+  const float mx0 = (t.u == 1) ? 2.0f : 1.0f, mx2 = (t.u == W - 2) ? 2.0f : 1.0f;
+  for (int q = t.warp; q < C::TH; q += C::NW) {
+    const int py = t.y0 + q;
+    if (!lane_ok || py >= H) continue;
+    const float my0 = (py == 1) ? 2.0f : 1.0f, my2 = (py == H - 2) ? 2.0f : 1.0f;
+    float sa[3] = {0, 0, 0}, sb[3] = {0, 0, 0}, sc[3] = {0, 0, 0};
+    bool any = false;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const float my = dy == 0 ? my0 : (dy == 2 ? my2 : 1.0f);
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int j = (q + dy) * C::P + t.lane + dx - 1;  // R1 row q+dy = centre row q+1 + (dy-1)
+        if (sm.bidx[j] != k) continue;
+        any = true;
+        const float m = my * (dx == 0 ? mx0 : (dx == 2 ? mx2 : 1.0f));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          sa[c] += m * sm.stash[(3 * c) * C::R1N + j];
+          sb[c] += m * sm.stash[(3 * c + 1) * C::R1N + j];
+          sc[c] += m * sm.stash[(3 * c + 2) * C::R1N + j];
+        }
+      }
+    }
+    if (!any) continue;
+    const int ctr2 = (q + 2) * C::P + t.lane;
+    const bool own = sm.bidx[(q + 1) * C::P + t.lane] == k;
+    float gpred[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float x = pred[c * C::R2N + ctr2], y = sm.tgt[c * C::R2N + ctr2];
+      float g = sa[c] + sb[c] * x + sc[c] * y;
+      if (own) {
+        const float d = sub(y, x);  // l1 = |target - pred|; abs'(0) = 0
+        g += (d > 0.0f) ? -g_l1 : ((d < 0.0f) ? g_l1 : 0.0f);
+      }
+      gpred[c] = g;
+    }
+    Sample s;
+    project_pixel(cam, t.px, py, depth[py * W + t.px], W, H, s);
+    Taps tp;
+    make_taps(s, W, H, tp);
+    float gix = 0.0f, giy = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) tap_channel_grad(src + c * HW, s, tp, gpred[c], gix, giy);
+    float gdep = 0.0f;
+    chain_to_depth_pose(cam, s, gix, giy, gdep, gP);
+    sm.gd[q * C::P + t.lane] += gdep;
+  }
+}
+
+template <class C>
+BBD_HD void rs_store_gdepth(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t) {
+  const int H = a.height, W = a.width;
+  float* out = a.gdepth + ((size_t)t.s * a.batch + t.b) * H * W;
+  if (t.lane < 2 || t.lane > 29 || t.u >= W) return;
+  for (int q = t.warp; q < C::TH; q += C::NW) {
+    const int py = t.y0 + q;
+    if (py < H) out[py * W + t.u] = sm.gd[q * C::P + t.lane];
+  }
+}
+
+// block reduction helpers shared with bbd_tile.cuh semantics (fixed order, no shuffles)
+template <class C, int K>
+BBD_HD void rs_park(float* red, int tid, const float* v) {
+#pragma unroll
+  for (int i = 0; i < K; ++i) red[i * C::NT + tid] = v[i];
+}
+template <class C, int K>
+BBD_HD void rs_level1(float* red, int tid) {
+  constexpr int SEGS = C::NT / C::RED_SEG;
+  if (tid < K * SEGS) {
+    const int comp = tid / SEGS, seg = tid % SEGS;
+    const float* src = red + comp * C::NT + seg * C::RED_SEG;
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < C::RED_SEG; ++i) s += src[i];
+    red[12 * C::NT + comp * C::RED_SEG * 2 + seg] = s;
+  }
+}
+template <class C, int K>
+BBD_HD void rs_level2(const float* red, int tid, float* out) {
+  constexpr int SEGS = C::NT / C::RED_SEG;
+  if (tid < K) {
+    const float* src = red + 12 * C::NT + tid * C::RED_SEG * 2;
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < SEGS; ++i) s += src[i];
+    out[tid] = s;
+  }
+}
+
+}  // namespace bbd

@@ -210,16 +210,54 @@ def fused_losses(plan: LossPlan, target: torch.Tensor, frames: Dict, disps: Sequ
     return reproj, smooth, cfg["aux"]
 
 
-def pack_poses(plan: LossPlan, K: torch.Tensor, T: Dict, T_err: Optional[Dict] = None) -> torch.Tensor:
+class _PosePack(torch.autograd.Function):
+    """T (n_pose,4,4) -> P = (K[k_row] @ T)[:, :3, :] with ATen-bmm rounding; gradient to T."""
+
+    @staticmethod
+    def forward(ctx, T, K, k_row, be):
+        Tc, Kc = T.detach().contiguous(), K.detach().contiguous()
+        be.check_device(Tc, Kc, k_row)
+        n = Tc.shape[0]
+        P = torch.empty(n, 3, 4, device=T.device, dtype=torch.float32)
+        be.call("pose_pack_forward", n, C.c_void_p(Kc.data_ptr()), C.c_void_p(k_row.data_ptr()),
+                C.c_void_p(Tc.data_ptr()), C.c_void_p(P.data_ptr()))
+        ctx.save_for_backward(Kc, k_row)
+        ctx.be = be
+        return P
+
+    @staticmethod
+    def backward(ctx, gP):
+        Kc, k_row = ctx.saved_tensors
+        g = gP.contiguous()
+        n = g.shape[0]
+        gT = torch.empty(n, 4, 4, device=g.device, dtype=torch.float32)
+        ctx.be.call("pose_pack_backward", n, C.c_void_p(Kc.data_ptr()), C.c_void_p(k_row.data_ptr()),
+                    C.c_void_p(g.data_ptr()), C.c_void_p(gT.data_ptr()))
+        return gT, None, None, None
+
+
+def pack_poses(plan: LossPlan, K: torch.Tensor, T: Dict, T_err: Optional[Dict] = None,
+               backend: Optional[_lib.Backend] = None) -> torch.Tensor:
     """Pack ``P = (K[:n] @ T_f)[:, :3, :]`` of every frame in ``plan.pose_slices()`` order.
 
     ``K[:n]`` (first n rows, not the selected samples' rows) is what the reference pairs
-    with a frame's poses (``trainer.py:431``, ``layers.py:182``).
+    with a frame's poses (``trainer.py:431``, ``layers.py:182``).  One concatenation and one
+    tiny kernel whose elements follow the k-sequential FMA chain of ATen's bmm.
     """
+    be = backend if backend is not None else _lib.cuda_backend()
     rows = []
     for f, is_err, lo, hi in plan.pose_slices():
-        src = T_err if is_err else T
-        Tf = src[f]
+        Tf = (T_err if is_err else T)[f]
         assert Tf.shape[0] == hi - lo, (f, Tf.shape, hi - lo)
-        rows.append(torch.matmul(K[: hi - lo], Tf)[:, :3, :])
-    return torch.cat(rows, 0) if rows else K.new_zeros(0, 3, 4)
+        rows.append(Tf)
+    if not rows:
+        return K.new_zeros(0, 3, 4)
+    T_all = torch.cat(rows, 0)
+    cache = getattr(plan, "_k_rows", None)
+    if cache is None or cache[0] != str(K.device):
+        idx = [i for f, is_err, lo, hi in plan.pose_slices() for i in range(hi - lo)]
+        cache = (str(K.device), torch.tensor(idx, dtype=torch.int32, device=K.device))
+        plan._k_rows = cache
+    if T_all.shape[0] == 0:
+        return K.new_zeros(0, 3, 4)
+    return _PosePack.apply(T_all, K, cache[1], be)

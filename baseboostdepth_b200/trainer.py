@@ -29,7 +29,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib
-from .fused import fused_losses, pack_poses
+from .fused import _PosePack, fused_losses, pack_poses
 from .plan import LossPlan, build_plan
 
 _PLAN_CACHE: Dict = {}
@@ -98,7 +98,7 @@ def loss_step(inputs, outputs, opt, plan: Optional[LossPlan] = None, noise=None,
 
     T = _frame_poses(plan, inputs, outputs, "cam_T_cam", row_masks)
     T_err = _frame_poses(plan, inputs, outputs, "cam_T_cam_error", row_masks) if plan.decomp else None
-    P = pack_poses(plan, inputs[("K", 0)], T, T_err)
+    P = pack_poses(plan, inputs[("K", 0)], T, T_err, backend=backend)
     frames = {f: inputs[("color", f, 0)] for f in plan.frames}
     disps = [outputs[("disp", s)] for s in scales]
     pyramid = [inputs[("color", 0, s)] for s in scales]
@@ -164,7 +164,11 @@ def materialise_warps(inputs, outputs, opt, plan: LossPlan, scales=None, backend
             for key, poses in (("color", T), ("color_D", T_err)):
                 if f not in poses:
                     continue
-                P = torch.matmul(K[:n], poses[f].detach())[:, :3, :].contiguous()
+                if n:
+                    k_row = torch.arange(n, dtype=torch.int32, device=color0.device)
+                    P = _PosePack.apply(poses[f].detach(), K, k_row, be)
+                else:
+                    P = K.new_zeros(0, 3, 4)
                 warped = torch.empty_like(images)
                 be.check_device(images, d, P)
                 if n:

@@ -109,6 +109,15 @@ int bbd_reproj_fused(const bbd_reproj_args* a, bbd_stream_t stream);
 /* loss (S) = sum(loss_part)/(B*H*W); gpose (S,num_pose,3,4) = sum over tiles. */
 int bbd_reproj_finalize(const bbd_reproj_args* a, float* loss, float* gpose, bbd_stream_t stream);
 
+/* ---- projection matrices -----------------------------------------------------
+ * layers.py:182: P = (K @ T)[:, :3, :] for every pose row, K row given per pose (the trainer
+ * pairs a frame's poses with K[:n], trainer.py:431).  Each element follows the rounding of
+ * ATen's CPU bmm for tiny matrices (multiply, add, k ascending; bit-identical to it).  backward: gT = K[:3,:]^T @ gP (rows 0..3). */
+int bbd_pose_pack_forward(int32_t n_pose, const float* K /* (B,4,4) */, const int32_t* k_row /* (n_pose) */,
+                          const float* T /* (n_pose,4,4) */, float* P /* (n_pose,3,4) */, bbd_stream_t stream);
+int bbd_pose_pack_backward(int32_t n_pose, const float* K, const int32_t* k_row, const float* gP /* (n_pose,3,4) */,
+                           float* gT /* (n_pose,4,4) */, bbd_stream_t stream);
+
 /* ---- warped images on demand ----------------------------------------------
  * outputs[("color",f,s)] for logging (trainer.py:722-726): same projection and
  * sampling as bbd_reproj_fused for one frame stack; pose rows / K rows are the

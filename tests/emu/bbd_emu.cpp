@@ -14,10 +14,13 @@
 
 #include "../../baseboostdepth_b200/csrc/bbd_ops.cuh"
 #include "../../baseboostdepth_b200/csrc/bbd_smooth.cuh"
+#include "../../baseboostdepth_b200/csrc/bbd_strip.cuh"
 #include "../../baseboostdepth_b200/csrc/bbd_tile.cuh"
 
 using namespace bbd;
 using Cfg = TileCfg<32, 16, 256>;
+using SCfg = StripCfg<20, 8>;
+#define FOR_STID for (int tid = 0; tid < SCfg::NT; ++tid)
 #define FOR_TID for (int tid = 0; tid < Cfg::NT; ++tid)
 
 extern "C" {
@@ -38,7 +41,7 @@ long emu_div_const_mismatches(float d) {
 }
 
 int emu_reproj_tiles(int32_t height, int32_t width) {
-  return ((width + Cfg::TW - 1) / Cfg::TW) * ((height + Cfg::TH - 1) / Cfg::TH);
+  return ((width + SCfg::TW - 1) / SCfg::TW) * ((height + SCfg::TH - 1) / SCfg::TH);
 }
 
 int emu_ident_forward(const bbd_ident_args* ap) {
@@ -69,43 +72,45 @@ int emu_ident_forward(const bbd_ident_args* ap) {
 
 int emu_reproj_fused(const bbd_reproj_args* ap) {
   const bbd_reproj_args& a = *ap;
-  std::vector<float> smem(ReprojSmem<Cfg>::floats(a.max_rep));
-  std::vector<float> gPs((size_t)Cfg::NT * 12);
-  const int gx = (a.width + Cfg::TW - 1) / Cfg::TW, gy = (a.height + Cfg::TH - 1) / Cfg::TH;
+  std::vector<float> smem(StripSmem<SCfg>::floats(a.max_rep));
+  std::vector<float> gPs((size_t)SCfg::NT * 12);
+  std::vector<StripCtx> ctx(SCfg::NT);
+  const int gx = (a.width + SCfg::TW - 1) / SCfg::TW, gy = (a.height + SCfg::TH - 1) / SCfg::TH;
   for (int bz = 0; bz < a.num_scales * a.batch; ++bz)
     for (int by = 0; by < gy; ++by)
       for (int bx = 0; bx < gx; ++bx) {
-        ReprojSmem<Cfg> sm;
+        StripSmem<SCfg> sm;
         sm.carve(smem.data(), a.max_rep);
-        TileId t = make_tile(bx, by, bz, a.batch, a.height, a.width, Cfg::TW, Cfg::TH);
-        const int n_rep = a.tab.hdr[(size_t)t.b * 4];
-        FOR_TID rp_load_target<Cfg>(a, sm, t, tid);
-        FOR_TID rp_target_stats<Cfg>(a, sm, t, tid);
+        FOR_STID ctx[tid] = make_strip<SCfg>(bx, by, bz, tid, a.batch, a.height, a.width);
+        const StripCtx& t0 = ctx[0];
+        const int n_rep = a.tab.hdr[(size_t)t0.b * 4];
+        FOR_STID rs_load_target<SCfg>(a, sm, ctx[tid], tid);
+        FOR_STID rs_target_stats<SCfg>(a, sm, ctx[tid]);
         for (int k = 0; k < n_rep; ++k) {
-          FOR_TID rp_warp<Cfg>(a, sm, t, k, tid);
-          FOR_TID rp_stats<Cfg>(a, sm, t, k, tid);
+          FOR_STID rs_warp<SCfg>(a, sm, ctx[tid], k);
+          FOR_STID rs_stats<SCfg>(a, sm, ctx[tid], k);
         }
-        FOR_TID {
-          const float part = rp_select<Cfg>(a, sm, t, n_rep, tid);
-          red_park<Cfg, 1>(sm.red, tid, &part);
+        FOR_STID {
+          const float part = rs_select<SCfg>(a, sm, ctx[tid], n_rep);
+          rs_park<SCfg, 1>(sm.red, tid, &part);
         }
-        FOR_TID red_level1<Cfg, 1>(sm.red, tid);
-        FOR_TID red_level2<Cfg, 1>(sm.red, tid, a.loss_part + ((size_t)t.s * a.batch + t.b) * t.ntiles + t.tile);
+        FOR_STID rs_level1<SCfg, 1>(sm.red, tid);
+        FOR_STID rs_level2<SCfg, 1>(sm.red, tid, a.loss_part + ((size_t)t0.s * a.batch + t0.b) * t0.ntiles + t0.tile);
         if (!a.need_grad) continue;
         for (int k = 0; k < BBD_MAX_REP; ++k) {
-          float* out = a.gpose_part + ((((size_t)t.s * a.batch + t.b) * BBD_MAX_REP + k) * t.ntiles + t.tile) * 12;
+          float* out = a.gpose_part + ((((size_t)t0.s * a.batch + t0.b) * BBD_MAX_REP + k) * t0.ntiles + t0.tile) * 12;
           if (k >= n_rep || !sm.anywin[k]) {
             for (int i = 0; i < 12; ++i) out[i] = 0.0f;
             continue;
           }
-          FOR_TID {
-            rp_backward<Cfg>(a, sm, t, k, tid, &gPs[(size_t)tid * 12]);
-            red_park<Cfg, 12>(sm.red, tid, &gPs[(size_t)tid * 12]);
+          FOR_STID {
+            rs_backward<SCfg>(a, sm, ctx[tid], k, &gPs[(size_t)tid * 12]);
+            rs_park<SCfg, 12>(sm.red, tid, &gPs[(size_t)tid * 12]);
           }
-          FOR_TID red_level1<Cfg, 12>(sm.red, tid);
-          FOR_TID red_level2<Cfg, 12>(sm.red, tid, out);
+          FOR_STID rs_level1<SCfg, 12>(sm.red, tid);
+          FOR_STID rs_level2<SCfg, 12>(sm.red, tid, out);
         }
-        FOR_TID rp_store_gdepth<Cfg>(a, sm, t, tid);
+        FOR_STID rs_store_gdepth<SCfg>(a, sm, ctx[tid]);
       }
   return 0;
 }
@@ -213,6 +218,17 @@ int emu_disp_to_depth_backward(const bbd_d2d_args* ap) {
     for (int b = 0; b < a.batch; ++b)
       for (int i = 0; i < h * w; ++i) a.gdisp[lvl][(size_t)b * h * w + i] = d2d_backward_px(a, lvl, b, i / w, i % w);
   }
+  return 0;
+}
+
+int emu_pose_pack_forward(int32_t n, const float* K, const int32_t* k_row, const float* T, float* P) {
+  for (int i = 0; i < n * 12; ++i)
+    P[i] = pose_pack_elem(K + (size_t)k_row[i / 12] * 16, T + (size_t)(i / 12) * 16, (i % 12) / 4, i % 4);
+  return 0;
+}
+int emu_pose_pack_backward(int32_t n, const float* K, const int32_t* k_row, const float* gP, float* gT) {
+  for (int i = 0; i < n * 16; ++i)
+    gT[i] = pose_pack_grad_elem(K + (size_t)k_row[i / 16] * 16, gP + (size_t)(i / 16) * 12, (i % 16) / 4, i % 4);
   return 0;
 }
 

@@ -37,3 +37,31 @@ def run_fused(inputs, outputs, opt, noise, num_scales, backend=None, groups=None
 
 def to_device(d, device):
     return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in d.items()}
+
+
+def mirror_to_device(inputs, outputs, params, device):
+    """Copy a CPU batch to the GPU so that the hot path sees *identical* inputs: the camera motions
+    are the CPU-assembled matrices (sin/cos differ by ulps between CPU and CUDA, and white-noise
+    images amplify an ulp of pose into 1e-4 of warped intensity), fed as leaves.  Returns
+    (inputs, outputs, leaves) where leaves maps ("disp", s) / ("cam_T_cam", 0, f) to GPU leaf tensors."""
+    gi = to_device(inputs, device)
+    go, leaves = {}, {}
+    for k, v in outputs.items():
+        if k[0] == "disp":
+            t = v.detach().to(device).requires_grad_(True)
+            go[k], leaves[k] = t, t
+        elif k[0] == "cam_T_cam":
+            t = v.detach().to(device)
+            if t.numel():
+                t.requires_grad_(True)
+                leaves[k] = t
+            go[k] = t
+        elif k[0] == "cam_T_cam_error":
+            go[k] = v.detach().to(device)
+    return gi, go, leaves
+
+
+def retain_pose_grads(outputs):
+    for k, v in outputs.items():
+        if k[0] == "cam_T_cam" and v.requires_grad and v.numel():
+            v.retain_grad()

@@ -9,7 +9,7 @@ import torch
 
 from baseboostdepth_b200.synthetic import make_batch, make_noise
 from baseboostdepth_b200.trainer import materialise_warps, plan_for
-from fused_util import run_fused, to_device
+from fused_util import mirror_to_device, retain_pose_grads, run_fused, to_device
 from helpers import Golden, assert_grad_parity, golden_cases, max_abs, pixel_agreement, rel_l2
 from oracle import loss_path as O
 
@@ -17,7 +17,8 @@ pytestmark = pytest.mark.gpu
 CASES = golden_cases()
 
 
-def _selection_check(win, plan, aux, scales):
+def _selection_check(win, plan, aux, scales, exact=False):
+    """argmin planes equal the oracle's wherever its best-vs-runner-up margin exceeds 1e-6."""
     order = [b for grp in aux["groups"] for b in plan.group_members[grp]]
     for i, s in enumerate(scales):
         args = torch.cat(aux["argmin"][s], 0)
@@ -36,24 +37,28 @@ def _selection_check(win, plan, aux, scales):
 @pytest.mark.parametrize("case", CASES)
 def test_golden_case_on_gpu(case, cuda_device):
     g = Golden(case)
+    retain_pose_grads(g.outputs)
     ref, aux = O.run(g.inputs, g.outputs, g.opt(), g.noise, num_scales=g.num_scales)
     ref["loss"].backward()
     g64 = Golden(case, dtype=torch.float64)
+    retain_pose_grads(g64.outputs)
     ref64, _ = O.run(g64.inputs, g64.outputs, g64.opt(), g64.noise, num_scales=g.num_scales)
     ref64["loss"].backward()
 
-    h = Golden(case, device=cuda_device)
+    h = Golden(case)
+    hi, ho, leaves = mirror_to_device(h.inputs, h.outputs, h.params, cuda_device)
     noise = {k: v.to(cuda_device) for k, v in h.noise.items()}
-    losses, plan = run_fused(h.inputs, h.outputs, h.opt(), noise, h.num_scales, groups=aux["groups"])
+    losses, plan = run_fused(hi, ho, h.opt(), noise, h.num_scales, groups=aux["groups"])
     for k, v in g.losses.items():
         assert abs(float(losses[k]) - v) <= 2e-6 * max(1.0, abs(v)), (k, float(losses[k]), v)
     losses["loss"].backward()
     torch.cuda.synchronize()
-    for k, p in g.params.items():
-        if p.grad is None:
-            continue
-        assert_grad_parity(h.params[k].grad, p.grad, g64.params[k].grad, k)
-    _selection_check(h.outputs["argmin"], plan, aux, h.scales)
+    for k, leaf in leaves.items():
+        ref32 = g.params[k].grad if k[0] == "disp" else g.outputs[k].grad
+        ref64_ = g64.params[k].grad if k[0] == "disp" else g64.outputs[k].grad
+        assert_grad_parity(leaf.grad, ref32, ref64_, k)
+    _selection_check(ho["argmin"], plan, aux, h.scales, exact=True)
+    h.inputs, h.outputs = hi, ho
     with torch.no_grad():
         materialise_warps(h.inputs, h.outputs, h.opt(), plan)
     s0 = h.scales[0]
@@ -82,26 +87,28 @@ def test_full_size_against_oracle(name, cfg, cuda_device):
     plan = plan_for(inputs["ordering"], opt.trimin, opt.decomp,
                     inputs[("color", "s", 0)].shape[0] if ("color", "s", 0) in inputs else None)
     noise = make_noise(plan, cfg["height"], cfg["width"], seed=5)
+    retain_pose_grads(outputs)
     ref, aux = O.run(inputs, outputs, opt, noise, num_scales=4)
     ref["loss"].backward()
     i64, o64, p64 = make_batch(seed=21, device="cpu", dtype=torch.float64, scales=scales, **cfg)
+    retain_pose_grads(o64)
     ref64, _ = O.run(i64, o64, opt, {k: v.double() for k, v in noise.items()}, num_scales=4)
     ref64["loss"].backward()
 
-    gi, go, gp = make_batch(seed=21, device=cuda_device, scales=scales, **cfg)
+    gi, go, leaves = mirror_to_device(inputs, outputs, params, cuda_device)
     gnoise = {k: v.to(cuda_device) for k, v in noise.items()}
     losses, plan = run_fused(gi, go, opt, gnoise, 4, groups=aux["groups"])
     losses["loss"].backward()
     torch.cuda.synchronize()
     for k in ref:
         assert abs(float(losses[k]) - float(ref[k])) <= 2e-6 * max(1.0, abs(float(ref[k]))), k
-    for k, p in params.items():
-        if p.grad is None:
-            continue
-        assert_grad_parity(gp[k].grad, p.grad, p64[k].grad, k)
+    for k, leaf in leaves.items():
+        ref32 = params[k].grad if k[0] == "disp" else outputs[k].grad
+        r64 = p64[k].grad if k[0] == "disp" else o64[k].grad
+        assert_grad_parity(leaf.grad, ref32, r64, k)
         if k[0] == "disp":   # per-pixel: all but the footprints of a few near-ties agree to 1e-4 of the peak
-            frac = pixel_agreement(gp[k].grad, p.grad, tol=1e-4)
-            assert frac <= 5e-3, (k, frac)
+            frac = pixel_agreement(leaf.grad, ref32, tol=1e-4)
+            assert frac <= 5e-3 * (1 + k[1]), (k, frac)
     _selection_check(go["argmin"], plan, aux, scales)
 
 
