@@ -15,7 +15,7 @@ import torch
 
 MAX_FRAMES, MAX_GROUPS, MAX_REP, MAX_IDENT, MAX_SCALES = 16, 8, 12, 6, 4
 LIB_NAME = "libbbd_loss.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+LIB_PATH = os.environ.get("BBD_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 fp = C.c_void_p
 

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "bbd_kernels.cu")
 OUT = os.path.join(HERE, "libbbd_loss.so")
 DEPS = [os.path.join(HERE, "csrc", f) for f in
-        ("bbd_kernels.cu", "bbd_common.cuh", "bbd_tile.cuh", "bbd_strip.cuh", "bbd_smooth.cuh", "bbd_ops.cuh")] + [
+        ("bbd_kernels.cu", "bbd_common.cuh", "bbd_strip.cuh", "bbd_smooth.cuh", "bbd_ops.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "bbd_loss.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -33,7 +33,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    extra = os.environ.get("BBD_NVCC_EXTRA", "").split()
+    out = os.environ.get("BBD_LIB_OUT", OUT)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

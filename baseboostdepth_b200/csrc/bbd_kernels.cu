@@ -9,15 +9,23 @@
 #include "bbd_ops.cuh"
 #include "bbd_smooth.cuh"
 #include "bbd_strip.cuh"
-#include "bbd_tile.cuh"
 
 namespace bbd {
 
-// Identity pre-pass: 32x16 target pixels per block of 256 threads.
-using Cfg = TileCfg<32, 16, 256>;
-// Fused loss: 28x20 target pixels per block of 8 warps, lanes = columns (bbd_strip.cuh).  With two
-// warped candidates the block needs ~91 KB of shared memory -> 2 blocks per SM.
-using SCfg = StripCfg<20, 8>;
+// Identity pre-pass and fused loss share one tile geometry: 28x16 target pixels per block of 8
+// warps, lanes = columns (bbd_strip.cuh).  With two warped candidates a block needs 64 KB of shared
+// memory and 80 registers per thread -> 3 blocks (24 warps) per SM, the best of the measured
+// variants (profiles/README.md).
+#ifndef BBD_TILE_H
+#define BBD_TILE_H 16
+#endif
+#ifndef BBD_MIN_BLOCKS
+#define BBD_MIN_BLOCKS 3
+#endif
+#ifndef BBD_WARPS
+#define BBD_WARPS 8
+#endif
+using SCfg = StripCfg<BBD_TILE_H, BBD_WARPS>;
 
 static thread_local char g_err[256] = "";
 
@@ -37,34 +45,34 @@ static int check_launch(const char* what) {
 // ------------------------------------------------------------------------------------------
 // identity pre-pass
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(Cfg::NT) ident_kernel(const bbd_ident_args a) {
+__global__ void __launch_bounds__(SCfg::NT) ident_kernel(const bbd_ident_args a) {
   extern __shared__ float smem[];
-  IdentSmem<Cfg> sm;
+  IdentStripSmem<SCfg> sm;
   sm.carve(smem);
   const int tid = threadIdx.x;
-  TileId t = make_tile(blockIdx.x, blockIdx.y, blockIdx.z, a.batch, a.height, a.width, Cfg::TW, Cfg::TH);
+  const StripCtx t = make_strip<SCfg>(blockIdx.x, blockIdx.y, blockIdx.z, tid, a.batch, a.height, a.width);
+  const int H = a.height, W = a.width;
   const int32_t* hdr = a.tab.hdr + (size_t)t.b * 4;
   const int n_id = hdr[1];
-  const float* noise = a.noise[hdr[2]] + (size_t)hdr[3] * a.height * a.width;
-  id_load<Cfg>(a, a.target + (size_t)t.b * 3 * a.height * a.width, sm.tgt, t, tid);
+  const float* noise = a.noise[hdr[2]] + (size_t)hdr[3] * H * W;
+  is_load<SCfg>(a.target + (size_t)t.b * 3 * H * W, sm.tgt, t, H, W);
   __syncthreads();
-  id_target_stats<Cfg>(a, sm, tid);
+  is_target_stats<SCfg>(a, sm, t);
   for (int j = 0; j < n_id; ++j) {
     const int32_t* e = a.tab.ident + ((size_t)t.b * BBD_MAX_IDENT + j) * 2;
-    const float* src = a.frames[e[0]] + (size_t)e[1] * 3 * a.height * a.width;
-    id_load<Cfg>(a, src, sm.src, t, tid);
+    is_load<SCfg>(a.frames[e[0]] + (size_t)e[1] * 3 * H * W, sm.src, t, H, W);
     __syncthreads();
-    id_candidate<Cfg>(a, sm, t, j, noise, tid);
+    is_candidate<SCfg>(a, sm, t, j, noise);
     __syncthreads();
   }
-  id_store<Cfg>(a, sm, t, tid);
+  is_store<SCfg>(a, sm, t);
 }
 
 // ------------------------------------------------------------------------------------------
 // fused reprojection loss
 // ------------------------------------------------------------------------------------------
 template <bool GRAD>
-__global__ void __launch_bounds__(SCfg::NT, 2) reproj_kernel(const bbd_reproj_args a) {
+__global__ void __launch_bounds__(SCfg::NT, BBD_MIN_BLOCKS) reproj_kernel(const bbd_reproj_args a) {
   extern __shared__ float smem[];
   StripSmem<SCfg> sm;
   sm.carve(smem, a.max_rep);
@@ -81,6 +89,7 @@ __global__ void __launch_bounds__(SCfg::NT, 2) reproj_kernel(const bbd_reproj_ar
     rs_stats<SCfg>(a, sm, t, k);
   }
   const float part = rs_select<SCfg>(a, sm, t, n_rep);
+  __syncthreads();  // the reduction scratch aliases the target statistics read by rs_select
   rs_park<SCfg, 1>(sm.red, tid, &part);
   __syncthreads();
   rs_level1<SCfg, 1>(sm.red, tid);
@@ -212,23 +221,29 @@ __global__ void __launch_bounds__(SM_NT) smooth_stage3_kernel(const SmoothArgs a
 // ------------------------------------------------------------------------------------------
 // element-wise operators
 // ------------------------------------------------------------------------------------------
-__global__ void d2d_forward_kernel(const bbd_d2d_args a) {
-  const int HW = a.height * a.width;
-  const size_t total = (size_t)a.levels * a.batch * HW;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int px = (int)(i % a.width), py = (int)((i / a.width) % a.height);
-    const int b = (int)((i / HW) % a.batch), lvl = (int)(i / ((size_t)HW * a.batch));
-    a.depth[i] = d2d_forward_px(a, lvl, b, py, px);
+// grid (blocks, 1, levels): the per-level interpolation scales are block constants
+__global__ void __launch_bounds__(256) d2d_forward_kernel(const bbd_d2d_args a) {
+  const int lvl = blockIdx.z;
+  const int H = a.height, W = a.width, HW = H * W;
+  const float sy = div_((float)a.h[lvl], (float)H), sx = div_((float)a.w[lvl], (float)W);
+  float* out = a.depth + (size_t)lvl * a.batch * HW;
+  const int total = a.batch * HW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / HW, r = i - b * HW;
+    const int py = r / W, px = r - py * W;
+    out[i] = d2d_forward_px(a, lvl, b, py, px, sy, sx);
   }
 }
 
-__global__ void d2d_backward_kernel(const bbd_d2d_args a) {
+__global__ void __launch_bounds__(128) d2d_backward_kernel(const bbd_d2d_args a) {
   const int lvl = blockIdx.z;
-  const int h = a.h[lvl], w = a.w[lvl];
-  const size_t total = (size_t)a.batch * h * w;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int ix = (int)(i % w), iy = (int)((i / w) % h), b = (int)(i / ((size_t)h * w));
-    a.gdisp[lvl][i] = d2d_backward_px(a, lvl, b, iy, ix);
+  const int h = a.h[lvl], w = a.w[lvl], hw = h * w;
+  const float sy = div_((float)h, (float)a.height), sx = div_((float)w, (float)a.width);
+  const int total = a.batch * hw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / hw, r = i - b * hw;
+    const int iy = r / w, ix = r - iy * w;
+    a.gdisp[lvl][i] = d2d_backward_px(a, lvl, b, iy, ix, sy, sx);
   }
 }
 
@@ -337,10 +352,10 @@ int bbd_reproj_tiles(int32_t height, int32_t width) {
 int bbd_ident_forward(const bbd_ident_args* a, bbd_stream_t stream) {
   if (!a || !a->target || !a->ident_min || !a->tab.hdr || !a->tab.ident) return fail(BBD_E_ARG, "ident: null argument");
   if (a->batch <= 0 || a->height < 2 || a->width < 2) return fail(BBD_E_ARG, "ident: bad size");
-  dim3 grid((a->width + Cfg::TW - 1) / Cfg::TW, (a->height + Cfg::TH - 1) / Cfg::TH, a->batch);
-  const size_t smem = IdentSmem<Cfg>::floats() * sizeof(float);
+  dim3 grid((a->width + SCfg::TW - 1) / SCfg::TW, (a->height + SCfg::TH - 1) / SCfg::TH, a->batch);
+  const size_t smem = IdentStripSmem<SCfg>::floats() * sizeof(float);
   cudaFuncSetAttribute(ident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  ident_kernel<<<grid, Cfg::NT, smem, (cudaStream_t)stream>>>(*a);
+  ident_kernel<<<grid, SCfg::NT, smem, (cudaStream_t)stream>>>(*a);
   return check_launch("ident_kernel");
 }
 
@@ -404,8 +419,9 @@ int bbd_disp_to_depth_forward(const bbd_d2d_args* a, bbd_stream_t stream) {
   if (a->levels < 1 || a->levels > BBD_MAX_SCALES) return fail(BBD_E_RANGE, "d2d: bad level count");
   for (int l = 0; l < a->levels; ++l)
     if (!a->disp[l] || a->h[l] < 1 || a->w[l] < 1) return fail(BBD_E_ARG, "d2d forward: bad level");
-  const size_t total = (size_t)a->levels * a->batch * a->height * a->width;
-  d2d_forward_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*a);
+  const size_t total = (size_t)a->batch * a->height * a->width;
+  dim3 grid(grid_for(total, 256), 1, a->levels);
+  d2d_forward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
   return check_launch("d2d_forward_kernel");
 }
 

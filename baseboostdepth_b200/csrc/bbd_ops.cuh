@@ -12,8 +12,8 @@ struct Lerp {
   int i0, i1;
   float l0, l1;
 };
-BBD_HD Lerp up_taps(int o, int in_size, int out_size) {
-  const float scale = div_((float)in_size, (float)out_size);
+// scale = float(in_size) / float(out_size), computed once per level (area_pixel_compute_scale)
+BBD_HD Lerp up_taps(int o, int in_size, float scale) {
   float src = sub(mul(scale, add((float)o, 0.5f)), 0.5f);
   if (src < 0.0f) src = 0.0f;
   Lerp t;
@@ -25,8 +25,8 @@ BBD_HD Lerp up_taps(int o, int in_size, int out_size) {
 }
 
 BBD_HD float d2d_up(const float* d, int w, const Lerp& ty, const Lerp& tx) {
-  const float* r0 = d + (size_t)ty.i0 * w;
-  const float* r1 = d + (size_t)ty.i1 * w;
+  const float* r0 = d + ty.i0 * w;
+  const float* r1 = d + ty.i1 * w;
   // rounding pattern of ATen's upsample_bilinear2d (checked bit-for-bit against torch CPU):
   // each lerp is fma(w0, a, RN(w1 * b))
   const float top = fma_(tx.l0, r0[tx.i0], mul(tx.l1, r0[tx.i1]));
@@ -35,10 +35,10 @@ BBD_HD float d2d_up(const float* d, int w, const Lerp& ty, const Lerp& tx) {
 }
 
 // one full-resolution pixel: upsample + disp_to_depth (layers.py:13-22)
-BBD_HD float d2d_forward_px(const bbd_d2d_args& a, int lvl, int b, int oy, int ox) {
+BBD_HD float d2d_forward_px(const bbd_d2d_args& a, int lvl, int b, int oy, int ox, float sy, float sx) {
   const int h = a.h[lvl], w = a.w[lvl];
   const float* d = a.disp[lvl] + (size_t)b * h * w;
-  const float up = d2d_up(d, w, up_taps(oy, h, a.height), up_taps(ox, w, a.width));
+  const float up = d2d_up(d, w, up_taps(oy, h, sy), up_taps(ox, w, sx));
   if (a.sql) return up;
   return div_(1.0f, add(a.min_disp, mul(a.disp_span, up)));
 }
@@ -47,42 +47,43 @@ BBD_HD float d2d_forward_px(const bbd_d2d_args& a, int lvl, int b, int oy, int o
 // For an integer factor f the pixel (iy, ix) is a tap of the outputs in [f*i - f, f*i + 2f);
 // the weight of output o for input i is l0 if i0 == i plus l1 if i1 == i (both can hold at the
 // clamped borders), exactly the transpose of d2d_up.
-BBD_HD float d2d_axis_weight(int o, int i, int in_size, int out_size) {
-  const Lerp t = up_taps(o, in_size, out_size);
+BBD_HD float d2d_axis_weight(int o, int i, int in_size, float scale) {
+  const Lerp t = up_taps(o, in_size, scale);
   return (t.i0 == i ? t.l0 : 0.0f) + (t.i1 == i ? t.l1 : 0.0f);
 }
 
-BBD_HD float d2d_backward_px(const bbd_d2d_args& a, int lvl, int b, int iy, int ix) {
+BBD_HD float d2d_backward_px(const bbd_d2d_args& a, int lvl, int b, int iy, int ix, float sy, float sx) {
   const int h = a.h[lvl], w = a.w[lvl], H = a.height, W = a.width;
   const float* gd = a.gdepth + ((size_t)lvl * a.batch + b) * H * W;
   const float* dep = a.depth + ((size_t)lvl * a.batch + b) * H * W;
-  const float span = a.disp_span;
+  const float nspan = -a.disp_span;
   float acc;
   if (h == H && w == W) {  // same resolution: the interpolation is the identity
-    const size_t o = (size_t)iy * W + ix;
+    const int o = iy * W + ix;
     acc = gd[o];
-    if (!a.sql) acc *= -span * dep[o] * dep[o];
+    if (!a.sql) acc *= nspan * dep[o] * dep[o];
   } else {
+    // src(o) = (o + 0.5)/f - 0.5 lies in (i-1, i+1) for o in [f*i - f/2, f*i + 3f/2 - 1]; one extra
+    // output on each side covers the clamped borders and rounding
     const int fy = H / h, fx = W / w;
-    int oy_lo = iy * fy - fy, oy_hi = iy * fy + 2 * fy;
-    int ox_lo = ix * fx - fx, ox_hi = ix * fx + 2 * fx;
+    int oy_lo = iy * fy - fy / 2 - 1, oy_hi = iy * fy + (3 * fy) / 2 + 1;
+    int ox_lo = ix * fx - fx / 2 - 1, ox_hi = ix * fx + (3 * fx) / 2 + 1;
     if (oy_lo < 0) oy_lo = 0;
     if (ox_lo < 0) ox_lo = 0;
     if (oy_hi > H) oy_hi = H;
     if (ox_hi > W) ox_hi = W;
-    float wxs[24];  // factor <= 8
-    const int nx = ox_hi - ox_lo;
-    for (int k = 0; k < 24; ++k) wxs[k] = (k < nx) ? d2d_axis_weight(ox_lo + k, ix, w, W) : 0.0f;
     acc = 0.0f;
     for (int oy = oy_lo; oy < oy_hi; ++oy) {
-      const float wy = d2d_axis_weight(oy, iy, h, H);
+      const float wy = d2d_axis_weight(oy, iy, h, sy);
       if (wy == 0.0f) continue;
       float row = 0.0f;
-      for (int k = 0; k < nx; ++k) {
-        const size_t o = (size_t)oy * W + ox_lo + k;
-        float g = gd[o];
-        if (!a.sql) g *= -span * dep[o] * dep[o];
-        row += wxs[k] * g;
+      const float* g = gd + oy * W;
+      const float* dp = dep + oy * W;
+      for (int ox = ox_lo; ox < ox_hi; ++ox) {
+        const float wx = d2d_axis_weight(ox, ix, w, sx);
+        float v = g[ox];
+        if (!a.sql) v *= nspan * dp[ox] * dp[ox];
+        row += wx * v;
       }
       acc += wy * row;
     }

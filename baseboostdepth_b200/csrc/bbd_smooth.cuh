@@ -7,7 +7,7 @@
 //   stage 1  per-chunk sums of disp                      -> sample mean m
 //   stage 2  per-pixel terms, loss partials, g_d = dL/d(norm disp), partials of sum(g_d * disp)
 //   stage 3  g_disp = g_d / (m+eps) - sum(g_d*disp) / (N (m+eps)^2); level loss
-// Same host/device phase structure as bbd_tile.cuh.
+// Same host/device phase structure as bbd_strip.cuh.
 #pragma once
 #include "bbd_common.cuh"
 
@@ -69,32 +69,33 @@ BBD_HD void sm_stage2_thread(const SmoothArgs& a, int lvl, int b, int chunk, int
   const float* img = a.img[lvl] + (size_t)b * 3 * n;
   float* g = a.gdisp[lvl] ? a.gdisp[lvl] + (size_t)b * n : nullptr;
   const float den = a.normalize ? add(mean, 1e-7f) : 1.0f;
+  const float rden = div_(1.0f, den);  // div_const(x, den, rden) == x / den up to rare last-bit cases
   const float inx = 1.0f / ((float)a.batch * (float)h * (float)(w - 1));
   const float iny = 1.0f / ((float)a.batch * (float)(h - 1) * (float)w);
   float stx = 0.0f, sty = 0.0f, sgd = 0.0f;
   for (int i = chunk * SM_CHUNK + tid; i < (chunk + 1) * SM_CHUNK && i < n; i += SM_NT) {
     const int x = i % w, y = i / w;
-    const float d0 = div_(d[i], den);
+    const float d0 = div_const(d[i], den, rden);
     float gd = 0.0f;
     if (x < w - 1) {
-      const float diff = sub(d0, div_(d[i + 1], den));
+      const float diff = sub(d0, div_const(d[i + 1], den, rden));
       const float e = sm_edge(img, n, i, i + 1);
       stx += mul(fabsf(diff), e);
       gd += (diff > 0.0f ? e : (diff < 0.0f ? -e : 0.0f)) * inx;
     }
     if (x > 0) {
-      const float diff = sub(div_(d[i - 1], den), d0);
+      const float diff = sub(div_const(d[i - 1], den, rden), d0);
       const float e = sm_edge(img, n, i - 1, i);
       gd -= (diff > 0.0f ? e : (diff < 0.0f ? -e : 0.0f)) * inx;
     }
     if (y < h - 1) {
-      const float diff = sub(d0, div_(d[i + w], den));
+      const float diff = sub(d0, div_const(d[i + w], den, rden));
       const float e = sm_edge(img, n, i, i + w);
       sty += mul(fabsf(diff), e);
       gd += (diff > 0.0f ? e : (diff < 0.0f ? -e : 0.0f)) * iny;
     }
     if (y > 0) {
-      const float diff = sub(div_(d[i - w], den), d0);
+      const float diff = sub(div_const(d[i - w], den, rden), d0);
       const float e = sm_edge(img, n, i - w, i);
       gd -= (diff > 0.0f ? e : (diff < 0.0f ? -e : 0.0f)) * iny;
     }

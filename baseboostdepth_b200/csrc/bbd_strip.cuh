@@ -4,7 +4,7 @@
 // the 32 columns of the tile's +-2 halo region (28 interior + 4 halo), warps stride over rows.
 // Every shared-memory plane has a row pitch of 32 floats, so a warp always touches 32
 // consecutive words (conflict-free) and no division / modulo is needed to find a slot.
-// Work is organised in phases separated by block barriers exactly like bbd_tile.cuh, and the
+// Work is organised in phases separated by block barriers and the
 // phase bodies are __host__ __device__ so tests/emu can step them on the CPU.
 //
 // Regions (padded image coordinates; reflection resolved when a value is produced):
@@ -13,6 +13,18 @@
 //   IN: rows 0..TH-1, lanes 2..29   pixels whose gradient we own  (IN row q = R2 row q+2)
 #pragma once
 #include "bbd_common.cuh"
+
+#ifndef BBD_UNROLL_WARP
+#define BBD_UNROLL_WARP 3
+#endif
+#ifndef BBD_UNROLL_STATS
+#define BBD_UNROLL_STATS 1
+#endif
+#ifndef BBD_UNROLL_BWD
+#define BBD_UNROLL_BWD 1
+#endif
+#define BBD_PRAGMA(x) _Pragma(#x)
+#define BBD_UNROLL(n) BBD_PRAGMA(unroll n)
 
 namespace bbd {
 
@@ -30,26 +42,26 @@ template <class C>
 struct StripSmem {
   float* tgt;    // [3][R2N]
   float* pred;   // [max_rep][3][R2N]
-  float* tst;    // [6][R1N]
+  float* tst;    // [6][R1N]  target window mean / variance term per channel
   float* stash;  // [9][R1N]  window sums of the best candidate -> gradient coefficients
   float* best;   // [R1N]
   int* bidx;     // [R1N]
   float* gd;     // [INN]
-  float* red;    // [12][NT] + [12][RED_SEG*2]
+  float* red;    // [12][NT] + [12][RED_SEG*2]; aliases tst (dead once the winners are selected)
   int* anywin;   // [BBD_MAX_REP]
+  static constexpr size_t RED = 12 * C::NT + 12 * C::RED_SEG * 2;
+  static constexpr size_t TST = (6 * C::R1N > RED) ? 6 * C::R1N : RED;
   static constexpr size_t floats(int max_rep) {
-    return 3 * C::R2N + (size_t)max_rep * 3 * C::R2N + 6 * C::R1N + 9 * C::R1N + 2 * C::R1N + C::INN + 12 * C::NT +
-           12 * C::RED_SEG * 2 + BBD_MAX_REP;
+    return 3 * C::R2N + (size_t)max_rep * 3 * C::R2N + TST + 9 * C::R1N + 2 * C::R1N + C::INN + BBD_MAX_REP;
   }
   BBD_HD void carve(float* base, int max_rep) {
     tgt = base; base += 3 * C::R2N;
     pred = base; base += (size_t)max_rep * 3 * C::R2N;
-    tst = base; base += 6 * C::R1N;
+    tst = base; red = base; base += TST;
     stash = base; base += 9 * C::R1N;
     best = base; base += C::R1N;
     bidx = reinterpret_cast<int*>(base); base += C::R1N;
     gd = base; base += C::INN;
-    red = base; base += 12 * C::NT + 12 * C::RED_SEG * 2;
     anywin = reinterpret_cast<int*>(base);
   }
 };
@@ -120,6 +132,8 @@ BBD_HD bool rs_center(const bbd_reproj_args& a, const StripCtx& t, int i, int& p
   return t.lane >= 1 && t.lane <= 30 && t.col_in && py >= 0 && py < a.height;
 }
 
+// Target window statistics, once per tile.  (Reading them precomputed from global memory was
+// measured slower: the tile's first phase is latency-bound and this arithmetic overlaps it.)
 template <class C>
 BBD_HD void rs_target_stats(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t) {
   if (a.no_ssim) return;
@@ -152,7 +166,11 @@ BBD_HD void rs_warp(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& 
   rs_candidate(a, t.b, k, src, cam);
   const float* depth = a.depth + ((size_t)t.s * a.batch + t.b) * HW;
   float* pred = sm.pred + (size_t)k * 3 * C::R2N;
-  for (int j = t.warp; j < C::R2H; j += C::NW) {
+  constexpr int ITERS = (C::R2H + C::NW - 1) / C::NW;
+  BBD_UNROLL(BBD_UNROLL_WARP)
+  for (int m = 0; m < ITERS; ++m) {
+    const int j = t.warp + m * C::NW;
+    if (C::R2H % C::NW != 0 && j >= C::R2H) break;
     const int py = reflect1(t.y0 - 2 + j, H);
     Sample s;
     project_pixel(cam, t.px, py, depth[py * W + t.px], W, H, s);
@@ -168,7 +186,11 @@ BBD_HD void rs_warp(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& 
 template <class C>
 BBD_HD void rs_stats(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t, int k) {
   const float* pred = sm.pred + (size_t)k * 3 * C::R2N;
-  for (int i = t.warp; i < C::R1H; i += C::NW) {
+  constexpr int ITERS = (C::R1H + C::NW - 1) / C::NW;
+  BBD_UNROLL(BBD_UNROLL_STATS)
+  for (int m = 0; m < ITERS; ++m) {
+    const int i = t.warp + m * C::NW;
+    if (i >= C::R1H) break;
     int py;
     if (!rs_center<C>(a, t, i, py)) continue;
     const int o = i * C::P + t.lane - 1;
@@ -282,7 +304,11 @@ BBD_HD void rs_backward(const bbd_reproj_args& a, StripSmem<C>& sm, const StripC
   const bool lane_ok = t.lane >= 2 && t.lane <= 29 && t.u < W;
   // multiplicity of a neighbouring window: a reflected border pixel sits twice in it
   const float mx0 = (t.u == 1) ? 2.0f : 1.0f, mx2 = (t.u == W - 2) ? 2.0f : 1.0f;
-  for (int q = t.warp; q < C::TH; q += C::NW) {
+  constexpr int ITERS = (C::TH + C::NW - 1) / C::NW;
+  BBD_UNROLL(BBD_UNROLL_BWD)
+  for (int m = 0; m < ITERS; ++m) {
+    const int q = t.warp + m * C::NW;
+    if (q >= C::TH) break;
     const int py = t.y0 + q;
     if (!lane_ok || py >= H) continue;
     const float my0 = (py == 1) ? 2.0f : 1.0f, my2 = (py == H - 2) ? 2.0f : 1.0f;
@@ -343,7 +369,114 @@ BBD_HD void rs_store_gdepth(const bbd_reproj_args& a, StripSmem<C>& sm, const St
   }
 }
 
-// block reduction helpers shared with bbd_tile.cuh semantics (fixed order, no shuffles)
+// ---------------------------------------------------------------------------------------
+// Identity pre-pass on the same tile geometry: min over the sample's sources of
+// (photometric(source, target) + noise), and the target window statistics for the main kernel.
+// ---------------------------------------------------------------------------------------
+template <class C>
+struct IdentStripSmem {
+  float* tgt;   // [3][R2N]
+  float* src;   // [3][R2N]
+  float* tst;   // [6][INN]
+  float* best;  // [INN]
+  int* arg;     // [INN]
+  static constexpr size_t floats() { return 6 * C::R2N + 8 * C::INN; }
+  BBD_HD void carve(float* base) {
+    tgt = base; base += 3 * C::R2N;
+    src = base; base += 3 * C::R2N;
+    tst = base; base += 6 * C::INN;
+    best = base; base += C::INN;
+    arg = reinterpret_cast<int*>(base);
+  }
+};
+
+template <class C>
+BBD_HD void is_load(const float* img, float* dst, const StripCtx& t, int H, int W) {
+  const int HW = H * W;
+  for (int j = t.warp; j < C::R2H; j += C::NW) {
+    const int o = reflect1(t.y0 - 2 + j, H) * W + t.px;
+    const int i = j * C::P + t.lane;
+    dst[i] = img[o];
+    dst[C::R2N + i] = img[HW + o];
+    dst[2 * C::R2N + i] = img[2 * HW + o];
+  }
+}
+
+template <class C>
+BBD_HD bool is_owned(const StripCtx& t, int q, int H, int W, int& py) {
+  py = t.y0 + q;
+  return t.lane >= 2 && t.lane <= 29 && t.u < W && py < H;
+}
+
+template <class C>
+BBD_HD void is_target_stats(const bbd_ident_args& a, IdentStripSmem<C>& sm, const StripCtx& t) {
+  if (a.no_ssim) return;
+  const int H = a.height, W = a.width;
+  for (int q = t.warp; q < C::TH; q += C::NW) {
+    int py;
+    if (!is_owned<C>(t, q, H, W, py)) continue;
+    const int o = (q + 1) * C::P + t.lane - 1;  // window top-left in R2 coordinates
+    const int j = q * C::P + t.lane;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* y = sm.tgt + c * C::R2N + o;
+      const WinY w = target_stats(w9(y), w9p(y, y));
+      sm.tst[(2 * c) * C::INN + j] = w.mu;
+      sm.tst[(2 * c + 1) * C::INN + j] = w.sig;
+    }
+  }
+}
+
+template <class C>
+BBD_HD void is_candidate(const bbd_ident_args& a, IdentStripSmem<C>& sm, const StripCtx& t, int jcand, const float* noise) {
+  const int H = a.height, W = a.width;
+  for (int q = t.warp; q < C::TH; q += C::NW) {
+    int py;
+    if (!is_owned<C>(t, q, H, W, py)) continue;
+    const int o = (q + 1) * C::P + t.lane - 1, ctr = o + C::P + 1;
+    const int j = q * C::P + t.lane;
+    float ssim_sum = 0.0f, l1_sum = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* x = sm.src + c * C::R2N;
+      const float* y = sm.tgt + c * C::R2N;
+      const float l1 = fabsf(sub(y[ctr], x[ctr]));
+      l1_sum = (c == 0) ? l1 : add(l1_sum, l1);
+      if (!a.no_ssim) {
+        WinX wx;
+        wx.sx = w9(x + o);
+        wx.sxx = w9p(x + o, x + o);
+        wx.sxy = w9p(x + o, y + o);
+        WinY wy;
+        wy.mu = sm.tst[(2 * c) * C::INN + j];
+        wy.sig = sm.tst[(2 * c + 1) * C::INN + j];
+        SsimParts parts;
+        const float v = ssim_channel(wx, wy, parts);
+        ssim_sum = (c == 0) ? v : add(ssim_sum, v);
+      }
+    }
+    const float loss = photometric_mix(ssim_sum, l1_sum, a.no_ssim != 0);
+    const float val = add(loss, mul(noise[py * W + t.u], a.noise_scale));
+    if (jcand == 0 || val < sm.best[j]) {
+      sm.best[j] = val;
+      sm.arg[j] = jcand;
+    }
+  }
+}
+
+template <class C>
+BBD_HD void is_store(const bbd_ident_args& a, IdentStripSmem<C>& sm, const StripCtx& t) {
+  const int H = a.height, W = a.width;
+  for (int q = t.warp; q < C::TH; q += C::NW) {
+    int py;
+    if (!is_owned<C>(t, q, H, W, py)) continue;
+    const size_t o = ((size_t)t.b * H + py) * W + t.u;
+    a.ident_min[o] = sm.best[q * C::P + t.lane];
+    if (a.ident_arg) a.ident_arg[o] = (uint8_t)sm.arg[q * C::P + t.lane];
+  }
+}
+
+// block reduction helpers (fixed order, no shuffles, no atomics)
 template <class C, int K>
 BBD_HD void rs_park(float* red, int tid, const float* v) {
 #pragma unroll

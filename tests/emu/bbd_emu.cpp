@@ -1,7 +1,7 @@
 // TEST-ONLY host harness: steps the thread-block phases of the sm_100a kernels on the CPU.
 //
 // The device kernels in baseboostdepth_b200/csrc/bbd_kernels.cu are thin drivers around the
-// __host__ __device__ phase functions of bbd_tile.cuh / bbd_smooth.cuh / bbd_ops.cuh.  This
+// __host__ __device__ phase functions of bbd_strip.cuh / bbd_smooth.cuh / bbd_ops.cuh.  This
 // file instantiates the same phase functions with g++ and runs, for every block, each
 // phase for tid = 0..NT-1 before moving to the next (a barrier between phases), so index
 // logic, halo/reflection handling, candidate tables and the analytic gradients can be
@@ -15,13 +15,13 @@
 #include "../../baseboostdepth_b200/csrc/bbd_ops.cuh"
 #include "../../baseboostdepth_b200/csrc/bbd_smooth.cuh"
 #include "../../baseboostdepth_b200/csrc/bbd_strip.cuh"
-#include "../../baseboostdepth_b200/csrc/bbd_tile.cuh"
 
 using namespace bbd;
-using Cfg = TileCfg<32, 16, 256>;
-using SCfg = StripCfg<20, 8>;
+#ifndef BBD_TILE_H
+#define BBD_TILE_H 16
+#endif
+using SCfg = StripCfg<BBD_TILE_H, 8>;
 #define FOR_STID for (int tid = 0; tid < SCfg::NT; ++tid)
-#define FOR_TID for (int tid = 0; tid < Cfg::NT; ++tid)
 
 extern "C" {
 
@@ -46,26 +46,28 @@ int emu_reproj_tiles(int32_t height, int32_t width) {
 
 int emu_ident_forward(const bbd_ident_args* ap) {
   const bbd_ident_args& a = *ap;
-  std::vector<float> smem(IdentSmem<Cfg>::floats());
-  const int gx = (a.width + Cfg::TW - 1) / Cfg::TW, gy = (a.height + Cfg::TH - 1) / Cfg::TH;
+  std::vector<float> smem(IdentStripSmem<SCfg>::floats());
+  std::vector<StripCtx> ctx(SCfg::NT);
+  const int H = a.height, W = a.width;
+  const int gx = (W + SCfg::TW - 1) / SCfg::TW, gy = (H + SCfg::TH - 1) / SCfg::TH;
   for (int bz = 0; bz < a.batch; ++bz)
     for (int by = 0; by < gy; ++by)
       for (int bx = 0; bx < gx; ++bx) {
-        IdentSmem<Cfg> sm;
+        IdentStripSmem<SCfg> sm;
         sm.carve(smem.data());
-        TileId t = make_tile(bx, by, bz, a.batch, a.height, a.width, Cfg::TW, Cfg::TH);
-        const int32_t* hdr = a.tab.hdr + (size_t)t.b * 4;
+        FOR_STID ctx[tid] = make_strip<SCfg>(bx, by, bz, tid, a.batch, H, W);
+        const int b = ctx[0].b;
+        const int32_t* hdr = a.tab.hdr + (size_t)b * 4;
         const int n_id = hdr[1];
-        const float* noise = a.noise[hdr[2]] + (size_t)hdr[3] * a.height * a.width;
-        FOR_TID id_load<Cfg>(a, a.target + (size_t)t.b * 3 * a.height * a.width, sm.tgt, t, tid);
-        FOR_TID id_target_stats<Cfg>(a, sm, tid);
+        const float* noise = a.noise[hdr[2]] + (size_t)hdr[3] * H * W;
+        FOR_STID is_load<SCfg>(a.target + (size_t)b * 3 * H * W, sm.tgt, ctx[tid], H, W);
+        FOR_STID is_target_stats<SCfg>(a, sm, ctx[tid]);
         for (int j = 0; j < n_id; ++j) {
-          const int32_t* e = a.tab.ident + ((size_t)t.b * BBD_MAX_IDENT + j) * 2;
-          const float* src = a.frames[e[0]] + (size_t)e[1] * 3 * a.height * a.width;
-          FOR_TID id_load<Cfg>(a, src, sm.src, t, tid);
-          FOR_TID id_candidate<Cfg>(a, sm, t, j, noise, tid);
+          const int32_t* e = a.tab.ident + ((size_t)b * BBD_MAX_IDENT + j) * 2;
+          FOR_STID is_load<SCfg>(a.frames[e[0]] + (size_t)e[1] * 3 * H * W, sm.src, ctx[tid], H, W);
+          FOR_STID is_candidate<SCfg>(a, sm, ctx[tid], j, noise);
         }
-        FOR_TID id_store<Cfg>(a, sm, t, tid);
+        FOR_STID is_store<SCfg>(a, sm, ctx[tid]);
       }
   return 0;
 }
@@ -90,10 +92,9 @@ int emu_reproj_fused(const bbd_reproj_args* ap) {
           FOR_STID rs_warp<SCfg>(a, sm, ctx[tid], k);
           FOR_STID rs_stats<SCfg>(a, sm, ctx[tid], k);
         }
-        FOR_STID {
-          const float part = rs_select<SCfg>(a, sm, ctx[tid], n_rep);
-          rs_park<SCfg, 1>(sm.red, tid, &part);
-        }
+        std::vector<float> parts(SCfg::NT);
+        FOR_STID parts[tid] = rs_select<SCfg>(a, sm, ctx[tid], n_rep);
+        FOR_STID rs_park<SCfg, 1>(sm.red, tid, &parts[tid]);
         FOR_STID rs_level1<SCfg, 1>(sm.red, tid);
         FOR_STID rs_level2<SCfg, 1>(sm.red, tid, a.loss_part + ((size_t)t0.s * a.batch + t0.b) * t0.ntiles + t0.tile);
         if (!a.need_grad) continue;
@@ -204,10 +205,12 @@ int emu_smooth_fused(const bbd_smooth_args* in) {
 int emu_disp_to_depth_forward(const bbd_d2d_args* ap) {
   const bbd_d2d_args& a = *ap;
   const int HW = a.height * a.width;
-  for (int lvl = 0; lvl < a.levels; ++lvl)
+  for (int lvl = 0; lvl < a.levels; ++lvl) {
+    const float sy = (float)a.h[lvl] / (float)a.height, sx = (float)a.w[lvl] / (float)a.width;
     for (int b = 0; b < a.batch; ++b)
       for (int i = 0; i < HW; ++i)
-        a.depth[((size_t)lvl * a.batch + b) * HW + i] = d2d_forward_px(a, lvl, b, i / a.width, i % a.width);
+        a.depth[((size_t)lvl * a.batch + b) * HW + i] = d2d_forward_px(a, lvl, b, i / a.width, i % a.width, sy, sx);
+  }
   return 0;
 }
 
@@ -215,8 +218,9 @@ int emu_disp_to_depth_backward(const bbd_d2d_args* ap) {
   const bbd_d2d_args& a = *ap;
   for (int lvl = 0; lvl < a.levels; ++lvl) {
     const int h = a.h[lvl], w = a.w[lvl];
+    const float sy = (float)h / (float)a.height, sx = (float)w / (float)a.width;
     for (int b = 0; b < a.batch; ++b)
-      for (int i = 0; i < h * w; ++i) a.gdisp[lvl][(size_t)b * h * w + i] = d2d_backward_px(a, lvl, b, i / w, i % w);
+      for (int i = 0; i < h * w; ++i) a.gdisp[lvl][(size_t)b * h * w + i] = d2d_backward_px(a, lvl, b, i / w, i % w, sy, sx);
   }
   return 0;
 }

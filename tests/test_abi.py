@@ -33,7 +33,7 @@ def test_library_exports_every_symbol(lib_path):
         assert hasattr(dll, sym), sym
     assert dll.bbd_version() == 1
     dll.bbd_reproj_tiles.restype = ctypes.c_int
-    assert dll.bbd_reproj_tiles(192, 640) == 23 * 10      # 28x20 tiles
+    assert dll.bbd_reproj_tiles(192, 640) == 23 * 12      # 28x16 tiles
 
 
 def test_struct_layouts_match_header(lib_path):
