@@ -247,6 +247,15 @@ __global__ void __launch_bounds__(128) d2d_backward_kernel(const bbd_d2d_args a)
   }
 }
 
+__global__ void pose_kernel(int n, const float* aa, const float* tr, int invert, float* T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pose_forward_one(aa + (size_t)i * 3, tr + (size_t)i * 3, invert, T + (size_t)i * 16);
+}
+__global__ void pose_grad_kernel(int n, const float* aa, const float* tr, int invert, const float* gT, float* gaa, float* gtr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pose_backward_one(aa + (size_t)i * 3, tr + (size_t)i * 3, invert, gT + (size_t)i * 16, gaa + (size_t)i * 3, gtr + (size_t)i * 3);
+}
+
 __global__ void pose_pack_kernel(int n, const float* K, const int32_t* k_row, const float* T, float* P) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * 12) return;
@@ -439,6 +448,23 @@ int bbd_disp_to_depth_backward(const bbd_d2d_args* a, bbd_stream_t stream) {
   dim3 grid(grid_for(most, 128), 1, a->levels);
   d2d_backward_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*a);
   return check_launch("d2d_backward_kernel");
+}
+
+int bbd_pose_forward(int32_t n, const float* axisangle, const float* translation, int32_t invert, float* T,
+                     bbd_stream_t stream) {
+  if (!axisangle || !translation || !T) return fail(BBD_E_ARG, "pose: null argument");
+  if (n <= 0) return 0;
+  pose_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(n, axisangle, translation, invert, T);
+  return check_launch("pose_kernel");
+}
+
+int bbd_pose_backward(int32_t n, const float* axisangle, const float* translation, int32_t invert, const float* gT,
+                      float* gaxisangle, float* gtranslation, bbd_stream_t stream) {
+  if (!axisangle || !translation || !gT || !gaxisangle || !gtranslation) return fail(BBD_E_ARG, "pose backward: null argument");
+  if (n <= 0) return 0;
+  pose_grad_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(n, axisangle, translation, invert, gT, gaxisangle,
+                                                                  gtranslation);
+  return check_launch("pose_grad_kernel");
 }
 
 int bbd_pose_pack_forward(int32_t n_pose, const float* K, const int32_t* k_row, const float* T, float* P,

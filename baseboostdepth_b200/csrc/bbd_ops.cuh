@@ -93,6 +93,94 @@ BBD_HD float d2d_backward_px(const bbd_d2d_args& a, int lvl, int b, int iy, int 
   return acc;
 }
 
+// ---- transformation_from_parameters (layers.py:25-100) ---------------------------------------
+// Value with three tangents (d/d axis-angle components); enough operators for the formulas.
+struct Dual3 {
+  float v, d[3];
+};
+BBD_HD Dual3 dconst(float v) { return Dual3{v, {0.0f, 0.0f, 0.0f}}; }
+BBD_HD Dual3 dvar(float v, int i) { Dual3 r = dconst(v); r.d[i] = 1.0f; return r; }
+BBD_HD Dual3 operator+(const Dual3& a, const Dual3& b) { return Dual3{add(a.v, b.v), {a.d[0] + b.d[0], a.d[1] + b.d[1], a.d[2] + b.d[2]}}; }
+BBD_HD Dual3 operator-(const Dual3& a, const Dual3& b) { return Dual3{sub(a.v, b.v), {a.d[0] - b.d[0], a.d[1] - b.d[1], a.d[2] - b.d[2]}}; }
+BBD_HD Dual3 operator*(const Dual3& a, const Dual3& b) {
+  return Dual3{mul(a.v, b.v), {a.d[0] * b.v + a.v * b.d[0], a.d[1] * b.v + a.v * b.d[1], a.d[2] * b.v + a.v * b.d[2]}};
+}
+BBD_HD Dual3 operator/(const Dual3& a, const Dual3& b) {
+  const float q = div_(a.v, b.v), ib = 1.0f / b.v;
+  return Dual3{q, {(a.d[0] - q * b.d[0]) * ib, (a.d[1] - q * b.d[1]) * ib, (a.d[2] - q * b.d[2]) * ib}};
+}
+
+// Rotation block of rot_from_axisangle (layers.py:61-100) as duals; R[r][c]
+BBD_HD void pose_rotation(const float* v, Dual3 R[3][3]) {
+  const Dual3 x0 = dvar(v[0], 0), y0 = dvar(v[1], 1), z0 = dvar(v[2], 2);
+  // angle = ||v||  (torch.norm: sqrt of the sum of squares)
+  const float n2 = add(add(mul(v[0], v[0]), mul(v[1], v[1])), mul(v[2], v[2]));
+  Dual3 angle;
+  angle.v = sqrtf(n2);
+  for (int i = 0; i < 3; ++i) angle.d[i] = angle.v > 0.0f ? v[i] / angle.v : 0.0f;
+  const Dual3 den = angle + dconst(1e-7f);
+  const Dual3 x = x0 / den, y = y0 / den, z = z0 / den;
+  Dual3 ca, sa;
+  ca.v = cosf(angle.v);
+  sa.v = sinf(angle.v);
+  for (int i = 0; i < 3; ++i) { ca.d[i] = -sa.v * angle.d[i]; sa.d[i] = ca.v * angle.d[i]; }
+  const Dual3 C = dconst(1.0f) - ca;
+  const Dual3 xs = x * sa, ys = y * sa, zs = z * sa;
+  const Dual3 xC = x * C, yC = y * C, zC = z * C;
+  const Dual3 xyC = x * yC, yzC = y * zC, zxC = z * xC;
+  R[0][0] = x * xC + ca; R[0][1] = xyC - zs;    R[0][2] = zxC + ys;
+  R[1][0] = xyC + zs;    R[1][1] = y * yC + ca; R[1][2] = yzC - xs;
+  R[2][0] = zxC - ys;    R[2][1] = yzC + xs;    R[2][2] = z * zC + ca;
+}
+
+// forward: T (row-major 4x4).  Non-inverted: T @ R = [R | t]; inverted: R^T @ T(-t) = [R^T | R^T(-t)],
+// the last column accumulated like the 4x4 matmul (k ascending, multiply then add).
+BBD_HD void pose_forward_one(const float* aa, const float* tr, int invert, float* T) {
+  Dual3 R[3][3];
+  pose_rotation(aa, R);
+  for (int i = 0; i < 16; ++i) T[i] = 0.0f;
+  T[15] = 1.0f;
+  if (!invert) {
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) T[r * 4 + c] = R[r][c].v;
+      T[r * 4 + 3] = tr[r];
+    }
+  } else {
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) T[r * 4 + c] = R[c][r].v;
+      float acc = mul(R[0][r].v, mul(tr[0], -1.0f));
+      acc = add(acc, mul(R[1][r].v, mul(tr[1], -1.0f)));
+      acc = add(acc, mul(R[2][r].v, mul(tr[2], -1.0f)));
+      T[r * 4 + 3] = acc;
+    }
+  }
+}
+
+BBD_HD void pose_backward_one(const float* aa, const float* tr, int invert, const float* gT, float* gaa, float* gtr) {
+  Dual3 R[3][3];
+  pose_rotation(aa, R);
+  float ga[3] = {0.0f, 0.0f, 0.0f}, gt[3] = {0.0f, 0.0f, 0.0f};
+  if (!invert) {
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c)
+        for (int i = 0; i < 3; ++i) ga[i] += gT[r * 4 + c] * R[r][c].d[i];
+      gt[r] = gT[r * 4 + 3];
+    }
+  } else {
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c)
+        for (int i = 0; i < 3; ++i) ga[i] += gT[r * 4 + c] * R[c][r].d[i];
+      // T[r][3] = -sum_k R[k][r] * t[k]
+      const float g = gT[r * 4 + 3];
+      for (int k = 0; k < 3; ++k) {
+        gt[k] -= g * R[k][r].v;
+        for (int i = 0; i < 3; ++i) ga[i] -= g * tr[k] * R[k][r].d[i];
+      }
+    }
+  }
+  for (int i = 0; i < 3; ++i) { gaa[i] = ga[i]; gtr[i] = gt[i]; }
+}
+
 // ---- P = (K @ T)[:3] (layers.py:182), one output element.  For these tiny batched 4x4 products
 // ATen's CPU bmm takes its naive loop (separately rounded multiply and add, k ascending) -- checked
 // bit-for-bit; the large (3x4)@(4xHW) products go through the FMA chain used in project_pixel.

@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import _lib
 from .geometry import (Conv3x3, ConvBlock, compute_depth_errors, disp_to_depth,  # noqa: F401  (re-exported)
-                       get_translation_matrix, rot_from_axisangle, transformation_from_parameters, upsample)
+                       get_translation_matrix, rot_from_axisangle, upsample)
 
 _TEST_BACKEND = None  # tests/ may point this at the CPU emulation harness; the package never does
 
@@ -31,6 +31,42 @@ def _backend():
 
 def _p(t):
     return C.c_void_p(t.data_ptr() if t is not None else None)
+
+
+class _Pose(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, axisangle, translation, invert):
+        be = _backend()
+        aa = axisangle.detach().reshape(-1, 3).contiguous()
+        tr = translation.detach().reshape(-1, 3).contiguous()
+        be.check_device(aa, tr)
+        n = aa.shape[0]
+        T = torch.empty(n, 4, 4, device=aa.device, dtype=torch.float32)
+        be.call("pose_forward", n, _p(aa), _p(tr), int(invert), _p(T))
+        ctx.save_for_backward(aa, tr)
+        ctx.meta = (bool(invert), axisangle.shape, translation.shape)
+        return T
+
+    @staticmethod
+    def backward(ctx, gT):
+        be = _backend()
+        aa, tr = ctx.saved_tensors
+        invert, sa, st = ctx.meta
+        g = gT.contiguous()
+        gaa, gtr = torch.empty_like(aa), torch.empty_like(tr)
+        be.call("pose_backward", aa.shape[0], _p(aa), _p(tr), int(invert), _p(g), _p(gaa), _p(gtr))
+        return gaa.view(sa), gtr.view(st), None
+
+
+def transformation_from_parameters(axisangle, translation, invert=False):
+    """Network outputs ``(B,1,3)`` axis-angle and translation -> camera motion ``(B,4,4)``.
+
+    Reference ``layers.py:25-42`` (with ``rot_from_axisangle`` ``:61-100`` and
+    ``get_translation_matrix`` ``:45-58``): about forty tiny tensor kernels per call there, one
+    kernel forward and one backward here.  The plain tensor version stays available as
+    ``baseboostdepth_b200.geometry.transformation_from_parameters``.
+    """
+    return _Pose.apply(axisangle, translation, bool(invert))
 
 
 class _Backproject(torch.autograd.Function):

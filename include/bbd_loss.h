@@ -109,6 +109,16 @@ int bbd_reproj_fused(const bbd_reproj_args* a, bbd_stream_t stream);
 /* loss (S) = sum(loss_part)/(B*H*W); gpose (S,num_pose,3,4) = sum over tiles. */
 int bbd_reproj_finalize(const bbd_reproj_args* a, float* loss, float* gpose, bbd_stream_t stream);
 
+/* ---- camera motion from network outputs ---------------------------------------
+ * layers.py:25-100: transformation_from_parameters(axisangle, translation, invert) =
+ * get_translation_matrix(t) @ rot_from_axisangle(v), or R^T @ T(-t) when invert.  One thread per
+ * pose instead of ~40 tiny tensor kernels; the backward propagates forward-mode tangents through
+ * the same formulas.  axisangle, translation: (n,3); T: (n,4,4). */
+int bbd_pose_forward(int32_t n, const float* axisangle, const float* translation, int32_t invert, float* T,
+                     bbd_stream_t stream);
+int bbd_pose_backward(int32_t n, const float* axisangle, const float* translation, int32_t invert,
+                      const float* gT, float* gaxisangle, float* gtranslation, bbd_stream_t stream);
+
 /* ---- projection matrices -----------------------------------------------------
  * layers.py:182: P = (K @ T)[:, :3, :] for every pose row, K row given per pose (the trainer
  * pairs a frame's poses with K[:n], trainer.py:431).  Each element follows the rounding of

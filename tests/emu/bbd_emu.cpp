@@ -225,6 +225,16 @@ int emu_disp_to_depth_backward(const bbd_d2d_args* ap) {
   return 0;
 }
 
+int emu_pose_forward(int32_t n, const float* aa, const float* tr, int32_t invert, float* T) {
+  for (int i = 0; i < n; ++i) pose_forward_one(aa + (size_t)i * 3, tr + (size_t)i * 3, invert, T + (size_t)i * 16);
+  return 0;
+}
+int emu_pose_backward(int32_t n, const float* aa, const float* tr, int32_t invert, const float* gT, float* gaa, float* gtr) {
+  for (int i = 0; i < n; ++i)
+    pose_backward_one(aa + (size_t)i * 3, tr + (size_t)i * 3, invert, gT + (size_t)i * 16, gaa + (size_t)i * 3, gtr + (size_t)i * 3);
+  return 0;
+}
+
 int emu_pose_pack_forward(int32_t n, const float* K, const int32_t* k_row, const float* T, float* P) {
   for (int i = 0; i < n * 12; ++i)
     P[i] = pose_pack_elem(K + (size_t)k_row[i / 12] * 16, T + (size_t)(i / 12) * 16, (i % 12) / 4, i % 4);

@@ -158,3 +158,50 @@ def test_cuda_required():
     be = _lib.cuda_backend()
     with pytest.raises(RuntimeError):
         be.check_device(torch.zeros(1))
+
+
+@pytest.mark.parametrize("invert", [False, True])
+def test_pose_kernel_on_gpu(invert, cuda_device):
+    import baseboostdepth_b200.layers as L
+    from baseboostdepth_b200 import geometry as G
+    gen = torch.Generator().manual_seed(3)
+    aa0, tr0 = 0.2 * torch.randn(24, 1, 3, generator=gen), torch.randn(24, 1, 3, generator=gen)
+    w = torch.randn(24, 4, 4, generator=gen)
+    aa_c, tr_c = aa0.clone().requires_grad_(True), tr0.clone().requires_grad_(True)
+    Tc = G.transformation_from_parameters(aa_c, tr_c, invert)
+    (Tc * w).sum().backward()
+    aa_g, tr_g = aa0.to(cuda_device).requires_grad_(True), tr0.to(cuda_device).requires_grad_(True)
+    Tg = L.transformation_from_parameters(aa_g, tr_g, invert)
+    (Tg * w.to(cuda_device)).sum().backward()
+    assert max_abs(Tg, Tc) <= 5e-7
+    assert rel_l2(aa_g.grad, aa_c.grad) <= 1e-5 and rel_l2(tr_g.grad, tr_c.grad) <= 1e-5
+
+
+def test_tier_a_operators_on_gpu(cuda_device):
+    """Module-level drop-ins (layers.py names) against the oracle's ATen ops, on the device."""
+    import baseboostdepth_b200.layers as L
+    gen = torch.Generator().manual_seed(5)
+    n, H, W = 3, 48, 96
+    K = torch.tensor([[0.58 * W, 0, 0.5 * W, 0], [0, 1.92 * H, 0.5 * H, 0], [0, 0, 1, 0], [0, 0, 0, 1.0]]).repeat(n, 1, 1)
+    inv_K = torch.linalg.pinv(K)
+    from baseboostdepth_b200 import geometry as G
+    Tm = G.transformation_from_parameters(0.02 * torch.randn(n, 1, 3, generator=gen), 0.05 * torch.randn(n, 1, 3, generator=gen))
+    depth = 1 + 5 * torch.rand(n, 1, H, W, generator=gen)
+    x, y = torch.rand(n, 3, H, W, generator=gen), torch.rand(n, 3, H, W, generator=gen)
+    # oracle on CPU
+    d_c = depth.clone().requires_grad_(True)
+    pix_c = O.project(O.backproject(d_c, inv_K, H, W), K, Tm, H, W)
+    x_c = x.clone().requires_grad_(True)
+    s_c = O.ssim(x_c, y)
+    (pix_c.sum() + s_c.sum()).backward()
+    # kernels on GPU
+    dev = cuda_device
+    d_g = depth.to(dev).requires_grad_(True)
+    pix_g = L.Project3D(n, H, W)(L.BackprojectDepth(n, H, W)(d_g, inv_K.to(dev)), K.to(dev), Tm.to(dev))
+    x_g = x.to(dev).requires_grad_(True)
+    s_g = L.SSIM()(x_g, y.to(dev))
+    (pix_g.sum() + s_g.sum()).backward()
+    assert max_abs(pix_g, pix_c) <= 1e-6 and max_abs(s_g, s_c) <= 1e-6
+    assert rel_l2(d_g.grad, d_c.grad) <= 1e-5 and rel_l2(x_g.grad, x_c.grad) <= 2e-5
+    norm = torch.rand(n, 1, H, W, generator=gen)
+    assert abs(float(L.get_smooth_loss(norm.to(dev), x.to(dev))) - float(O.smooth_loss(norm, x))) <= 1e-6

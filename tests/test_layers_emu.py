@@ -117,8 +117,11 @@ def test_geometry_helpers_bit_identical():
         ref = importlib.import_module("layers")
     finally:
         sys.path.remove("/root/reference")
+    from baseboostdepth_b200 import geometry as G
     for inv in (False, True):
-        assert torch.equal(L.transformation_from_parameters(aa, tr, inv), ref.transformation_from_parameters(aa, tr, inv))
+        want = ref.transformation_from_parameters(aa, tr, inv)
+        assert torch.equal(G.transformation_from_parameters(aa, tr, inv), want)       # tensor version
+        assert max_abs(L.transformation_from_parameters(aa, tr, inv), want) <= 2e-7    # fused kernel
     d = torch.rand(2, 1, 4, 4, generator=g)
     assert torch.equal(L.disp_to_depth(d, 0.1, 100)[1], ref.disp_to_depth(d, 0.1, 100)[1])
 
@@ -169,3 +172,23 @@ def test_reference_trainer_runs_unchanged_on_drop_in_layers():
         sys.modules.pop("layers", None)
         if saved_layers is not None:
             sys.modules["layers"] = saved_layers
+
+
+@pytest.mark.parametrize("invert", [False, True])
+def test_pose_kernel_matches_tensor_version(invert):
+    from baseboostdepth_b200 import geometry as G
+    gen = torch.Generator().manual_seed(11)
+    aa0 = 0.3 * torch.randn(7, 1, 3, generator=gen)
+    aa0[0] = 0.0                                   # zero rotation: angle = 0 is a legal network output
+    tr0 = torch.randn(7, 1, 3, generator=gen)
+    w = torch.randn(7, 4, 4, generator=gen)
+    res = []
+    for fn in (G.transformation_from_parameters, L.transformation_from_parameters):
+        aa, tr = aa0.clone().requires_grad_(True), tr0.clone().requires_grad_(True)
+        T = fn(aa, tr, invert)
+        (T * w).sum().backward()
+        res.append((T.detach(), aa.grad, tr.grad))
+    assert max_abs(res[1][0], res[0][0]) <= 1e-6
+    assert rel_l2(res[1][1][1:], res[0][1][1:]) <= 1e-5
+    assert rel_l2(res[1][2], res[0][2]) <= 1e-5
+    assert torch.isfinite(res[1][1]).all()
