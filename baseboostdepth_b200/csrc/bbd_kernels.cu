@@ -71,6 +71,35 @@ __global__ void __launch_bounds__(SCfg::NT) ident_kernel(const bbd_ident_args a)
 // ------------------------------------------------------------------------------------------
 // fused reprojection loss
 // ------------------------------------------------------------------------------------------
+// Block sum of K per-thread values in a fixed order: xor-butterfly inside each warp, then the NW
+// warp partials are added by one thread per component.  No atomics.  red: [NW][12] floats.
+template <int K>
+__device__ __forceinline__ void block_reduce(float* red, int tid, const float* v, float* out) {
+  float r[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) r[i] = v[i];
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) r[i] += __shfl_xor_sync(0xffffffffu, r[i], off);
+  }
+  if ((tid & 31) == 0) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) red[(tid >> 5) * 12 + i] = r[i];
+  }
+  __syncthreads();
+  if (tid < K) {
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < SCfg::NW; ++w) s += red[w * 12 + tid];
+    out[tid] = s;
+  }
+  __syncthreads();
+}
+
+// grid (tiles_x, tiles_y, S*B): one block per tile of one (scale, sample).  (Walking over the four
+// scales inside one block to share the target tile was measured slower: 4x fewer blocks, more
+// live state -> spills at 80 registers.)
 template <bool GRAD>
 __global__ void __launch_bounds__(SCfg::NT, BBD_MIN_BLOCKS) reproj_kernel(const bbd_reproj_args a) {
   extern __shared__ float smem[];
@@ -81,37 +110,31 @@ __global__ void __launch_bounds__(SCfg::NT, BBD_MIN_BLOCKS) reproj_kernel(const 
   const int n_rep = a.tab.hdr[(size_t)t.b * 4];
 
   rs_load_target<SCfg>(a, sm, t, tid);
+  rs_begin_scale<SCfg>(sm, tid);
   __syncthreads();
   rs_target_stats<SCfg>(a, sm, t);
-  for (int k = 0; k < n_rep; ++k) {
-    rs_warp<SCfg>(a, sm, t, k);
-    __syncthreads();
-    rs_stats<SCfg>(a, sm, t, k);
-  }
-  const float part = rs_select<SCfg>(a, sm, t, n_rep);
-  __syncthreads();  // the reduction scratch aliases the target statistics read by rs_select
-  rs_park<SCfg, 1>(sm.red, tid, &part);
-  __syncthreads();
-  rs_level1<SCfg, 1>(sm.red, tid);
-  __syncthreads();
-  rs_level2<SCfg, 1>(sm.red, tid, a.loss_part + ((size_t)t.s * a.batch + t.b) * t.ntiles + t.tile);
-
-  if (GRAD) {
-    for (int k = 0; k < BBD_MAX_REP; ++k) {
-      float* out = a.gpose_part + ((((size_t)t.s * a.batch + t.b) * BBD_MAX_REP + k) * t.ntiles + t.tile) * 12;
-      if (k >= n_rep || !sm.anywin[k]) {  // block-uniform
-        if (tid < 12) out[tid] = 0.0f;
-        continue;
-      }
-      float gP[12];
-      rs_backward<SCfg>(a, sm, t, k, gP);
-      rs_park<SCfg, 12>(sm.red, tid, gP);
+  {
+    for (int k = 0; k < n_rep; ++k) {
+      rs_warp<SCfg>(a, sm, t, k);
       __syncthreads();
-      rs_level1<SCfg, 12>(sm.red, tid);
-      __syncthreads();
-      rs_level2<SCfg, 12>(sm.red, tid, out);
+      rs_stats<SCfg>(a, sm, t, k);
     }
-    rs_store_gdepth<SCfg>(a, sm, t);
+    const float part = rs_select<SCfg>(a, sm, t, n_rep);
+    block_reduce<1>(sm.red, tid, &part, a.loss_part + ((size_t)t.s * a.batch + t.b) * t.ntiles + t.tile);
+
+    if (GRAD) {
+      for (int k = 0; k < BBD_MAX_REP; ++k) {
+        float* out = a.gpose_part + ((((size_t)t.s * a.batch + t.b) * BBD_MAX_REP + k) * t.ntiles + t.tile) * 12;
+        if (k >= n_rep || !sm.anywin[k]) {  // block-uniform
+          if (tid < 12) out[tid] = 0.0f;
+          continue;
+        }
+        float gP[12];
+        rs_backward<SCfg>(a, sm, t, k, gP);
+        block_reduce<12>(sm.red, tid, gP, out);
+      }
+      rs_store_gdepth<SCfg>(a, sm, t);
+    }
   }
 }
 

@@ -47,21 +47,21 @@ struct StripSmem {
   float* best;   // [R1N]
   int* bidx;     // [R1N]
   float* gd;     // [INN]
-  float* red;    // [12][NT] + [12][RED_SEG*2]; aliases tst (dead once the winners are selected)
+  float* red;    // [NW][12] warp partials of the block reduction (the CPU harness brings its own scratch)
   int* anywin;   // [BBD_MAX_REP]
-  static constexpr size_t RED = 12 * C::NT + 12 * C::RED_SEG * 2;
-  static constexpr size_t TST = (6 * C::R1N > RED) ? 6 * C::R1N : RED;
   static constexpr size_t floats(int max_rep) {
-    return 3 * C::R2N + (size_t)max_rep * 3 * C::R2N + TST + 9 * C::R1N + 2 * C::R1N + C::INN + BBD_MAX_REP;
+    return 3 * C::R2N + (size_t)max_rep * 3 * C::R2N + 6 * C::R1N + 9 * C::R1N + 2 * C::R1N + C::INN + C::NW * 12 +
+           BBD_MAX_REP;
   }
   BBD_HD void carve(float* base, int max_rep) {
     tgt = base; base += 3 * C::R2N;
     pred = base; base += (size_t)max_rep * 3 * C::R2N;
-    tst = base; red = base; base += TST;
+    tst = base; base += 6 * C::R1N;
     stash = base; base += 9 * C::R1N;
     best = base; base += C::R1N;
     bidx = reinterpret_cast<int*>(base); base += C::R1N;
     gd = base; base += C::INN;
+    red = base; base += C::NW * 12;
     anywin = reinterpret_cast<int*>(base);
   }
 };
@@ -121,6 +121,11 @@ BBD_HD void rs_load_target(const bbd_reproj_args& a, StripSmem<C>& sm, const Str
     sm.tgt[C::R2N + i] = img[HW + o];
     sm.tgt[2 * C::R2N + i] = img[2 * HW + o];
   }
+}
+
+// per-scale reset of the accumulators
+template <class C>
+BBD_HD void rs_begin_scale(StripSmem<C>& sm, int tid) {
   if (tid < BBD_MAX_REP) sm.anywin[tid] = 0;
   for (int i = tid; i < C::INN; i += C::NT) sm.gd[i] = 0.0f;
 }

@@ -75,7 +75,8 @@ int emu_ident_forward(const bbd_ident_args* ap) {
 int emu_reproj_fused(const bbd_reproj_args* ap) {
   const bbd_reproj_args& a = *ap;
   std::vector<float> smem(StripSmem<SCfg>::floats(a.max_rep));
-  std::vector<float> gPs((size_t)SCfg::NT * 12);
+  std::vector<float> red(12 * SCfg::NT + 12 * SCfg::RED_SEG * 2);  // host-side reduction scratch
+  std::vector<float> gPs((size_t)SCfg::NT * 12), parts(SCfg::NT);
   std::vector<StripCtx> ctx(SCfg::NT);
   const int gx = (a.width + SCfg::TW - 1) / SCfg::TW, gy = (a.height + SCfg::TH - 1) / SCfg::TH;
   for (int bz = 0; bz < a.num_scales * a.batch; ++bz)
@@ -83,35 +84,39 @@ int emu_reproj_fused(const bbd_reproj_args* ap) {
       for (int bx = 0; bx < gx; ++bx) {
         StripSmem<SCfg> sm;
         sm.carve(smem.data(), a.max_rep);
+        sm.red = red.data();
         FOR_STID ctx[tid] = make_strip<SCfg>(bx, by, bz, tid, a.batch, a.height, a.width);
-        const StripCtx& t0 = ctx[0];
-        const int n_rep = a.tab.hdr[(size_t)t0.b * 4];
+        const int b = ctx[0].b, tile = ctx[0].tile, ntiles = ctx[0].ntiles;
+        const int n_rep = a.tab.hdr[(size_t)b * 4];
         FOR_STID rs_load_target<SCfg>(a, sm, ctx[tid], tid);
         FOR_STID rs_target_stats<SCfg>(a, sm, ctx[tid]);
-        for (int k = 0; k < n_rep; ++k) {
-          FOR_STID rs_warp<SCfg>(a, sm, ctx[tid], k);
-          FOR_STID rs_stats<SCfg>(a, sm, ctx[tid], k);
-        }
-        std::vector<float> parts(SCfg::NT);
-        FOR_STID parts[tid] = rs_select<SCfg>(a, sm, ctx[tid], n_rep);
-        FOR_STID rs_park<SCfg, 1>(sm.red, tid, &parts[tid]);
-        FOR_STID rs_level1<SCfg, 1>(sm.red, tid);
-        FOR_STID rs_level2<SCfg, 1>(sm.red, tid, a.loss_part + ((size_t)t0.s * a.batch + t0.b) * t0.ntiles + t0.tile);
-        if (!a.need_grad) continue;
-        for (int k = 0; k < BBD_MAX_REP; ++k) {
-          float* out = a.gpose_part + ((((size_t)t0.s * a.batch + t0.b) * BBD_MAX_REP + k) * t0.ntiles + t0.tile) * 12;
-          if (k >= n_rep || !sm.anywin[k]) {
-            for (int i = 0; i < 12; ++i) out[i] = 0.0f;
-            continue;
+        {
+          const int s = ctx[0].s;
+          FOR_STID rs_begin_scale<SCfg>(sm, tid);
+          for (int k = 0; k < n_rep; ++k) {
+            FOR_STID rs_warp<SCfg>(a, sm, ctx[tid], k);
+            FOR_STID rs_stats<SCfg>(a, sm, ctx[tid], k);
           }
-          FOR_STID {
-            rs_backward<SCfg>(a, sm, ctx[tid], k, &gPs[(size_t)tid * 12]);
-            rs_park<SCfg, 12>(sm.red, tid, &gPs[(size_t)tid * 12]);
+          FOR_STID parts[tid] = rs_select<SCfg>(a, sm, ctx[tid], n_rep);
+          FOR_STID rs_park<SCfg, 1>(sm.red, tid, &parts[tid]);
+          FOR_STID rs_level1<SCfg, 1>(sm.red, tid);
+          FOR_STID rs_level2<SCfg, 1>(sm.red, tid, a.loss_part + ((size_t)s * a.batch + b) * ntiles + tile);
+          if (!a.need_grad) continue;
+          for (int k = 0; k < BBD_MAX_REP; ++k) {
+            float* out = a.gpose_part + ((((size_t)s * a.batch + b) * BBD_MAX_REP + k) * ntiles + tile) * 12;
+            if (k >= n_rep || !sm.anywin[k]) {
+              for (int i = 0; i < 12; ++i) out[i] = 0.0f;
+              continue;
+            }
+            FOR_STID {
+              rs_backward<SCfg>(a, sm, ctx[tid], k, &gPs[(size_t)tid * 12]);
+              rs_park<SCfg, 12>(sm.red, tid, &gPs[(size_t)tid * 12]);
+            }
+            FOR_STID rs_level1<SCfg, 12>(sm.red, tid);
+            FOR_STID rs_level2<SCfg, 12>(sm.red, tid, out);
           }
-          FOR_STID rs_level1<SCfg, 12>(sm.red, tid);
-          FOR_STID rs_level2<SCfg, 12>(sm.red, tid, out);
+          FOR_STID rs_store_gdepth<SCfg>(a, sm, ctx[tid]);
         }
-        FOR_STID rs_store_gdepth<SCfg>(a, sm, ctx[tid]);
       }
   return 0;
 }
