@@ -52,6 +52,35 @@ BBD_HD float div_const(float a, float d, float y) {
   return fma_(r, y, q);
 }
 
+// ---- two values per lane -------------------------------------------------------------------
+// sm_100 issues packed fp32x2 multiply / add / fma (FMUL2, FADD2, FFMA2) with the same rounding as
+// the scalar forms at half the issue slots per value (scripts/micro/ffma2_bench.cu: packed
+// mul+add runs at 2x the scalar rate).  The statistics phase processes two rows per thread this way.
+struct f2 {
+  float x, y;
+};
+BBD_HD f2 mk2(float x, float y) { f2 r; r.x = x; r.y = y; return r; }
+BBD_HD f2 bc2(float v) { return mk2(v, v); }
+#if defined(__CUDA_ARCH__)
+BBD_HD float2 as_f2(const f2& a) { return make_float2(a.x, a.y); }
+BBD_HD f2 from_f2(const float2& a) { return mk2(a.x, a.y); }
+BBD_HD f2 mul(const f2& a, const f2& b) { return from_f2(__fmul2_rn(as_f2(a), as_f2(b))); }
+BBD_HD f2 add(const f2& a, const f2& b) { return from_f2(__fadd2_rn(as_f2(a), as_f2(b))); }
+BBD_HD f2 fma_(const f2& a, const f2& b, const f2& c) { return from_f2(__ffma2_rn(as_f2(a), as_f2(b), as_f2(c))); }
+BBD_HD f2 sub(const f2& a, const f2& b) { return from_f2(__fadd2_rn(as_f2(a), make_float2(-b.x, -b.y))); }
+#else
+BBD_HD f2 mul(const f2& a, const f2& b) { return mk2(a.x * b.x, a.y * b.y); }
+BBD_HD f2 add(const f2& a, const f2& b) { return mk2(a.x + b.x, a.y + b.y); }
+BBD_HD f2 fma_(const f2& a, const f2& b, const f2& c) { return mk2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+BBD_HD f2 sub(const f2& a, const f2& b) { return mk2(a.x - b.x, a.y - b.y); }
+#endif
+BBD_HD f2 div_(const f2& a, const f2& b) { return mk2(div_(a.x, b.x), div_(a.y, b.y)); }
+BBD_HD f2 div_const(const f2& a, float d, float y) {
+  const f2 q = mul(a, bc2(y));
+  const f2 r = fma_(bc2(-d), q, a);
+  return fma_(r, bc2(y), q);
+}
+
 // SSIM constants (layers.py:232-233), photometric mix (trainer.py:485)
 #define BBD_C1 0.0001f
 #define BBD_C2 0.0009f
@@ -229,6 +258,21 @@ BBD_HD float ssim_channel(const WinX& wx, const WinY& wy, SsimParts& q) {
   q.r = div_(mul(q.n1, q.n2), mul(q.d1, q.d2));
   q.raw = mul(sub(1.0f, q.r), 0.5f);
   return fminf(fmaxf(q.raw, 0.0f), 1.0f);
+}
+
+// Two window centres at once (same operation order, hence bit-identical to ssim_channel).
+BBD_HD f2 ninth(const f2& s) { return div_const(s, 9.0f, 0.111111111938953399658203125f); }
+BBD_HD f2 ssim_channel2(const f2& sx, const f2& sxx, const f2& sxy, const f2& muy, const f2& sigy) {
+  const f2 mux = ninth(sx);
+  const f2 sigx = sub(ninth(sxx), mul(mux, mux));
+  const f2 sigxy = sub(ninth(sxy), mul(mux, muy));
+  const f2 n1 = add(mul(mul(bc2(2.0f), mux), muy), bc2(BBD_C1));
+  const f2 n2 = add(mul(bc2(2.0f), sigxy), bc2(BBD_C2));
+  const f2 d1 = add(add(mul(mux, mux), mul(muy, muy)), bc2(BBD_C1));
+  const f2 d2 = add(add(sigx, sigy), bc2(BBD_C2));
+  const f2 r = div_(mul(n1, n2), mul(d1, d2));
+  const f2 raw = mul(sub(bc2(1.0f), r), bc2(0.5f));
+  return mk2(fminf(fmaxf(raw.x, 0.0f), 1.0f), fminf(fmaxf(raw.y, 0.0f), 1.0f));
 }
 
 // Coefficients (a, b, c) such that d(value)/d x(u) = a + b*x(u) + c*y(u) for every pixel u of

@@ -244,17 +244,42 @@ __global__ void __launch_bounds__(SM_NT) smooth_stage3_kernel(const SmoothArgs a
 // ------------------------------------------------------------------------------------------
 // element-wise operators
 // ------------------------------------------------------------------------------------------
-// grid (blocks, 1, levels): the per-level interpolation scales are block constants
+// grid (blocks, 1, levels): the per-level interpolation scales are block constants.  A thread
+// produces four consecutive pixels of a row (one 16-byte store when the row pitch allows), sharing
+// the row taps.
 __global__ void __launch_bounds__(256) d2d_forward_kernel(const bbd_d2d_args a) {
   const int lvl = blockIdx.z;
   const int H = a.height, W = a.width, HW = H * W;
-  const float sy = div_((float)a.h[lvl], (float)H), sx = div_((float)a.w[lvl], (float)W);
+  const int h = a.h[lvl], w = a.w[lvl];
+  const float sy = div_((float)h, (float)H), sx = div_((float)w, (float)W);
   float* out = a.depth + (size_t)lvl * a.batch * HW;
-  const int total = a.batch * HW;
+  const int gw = (W + 3) / 4;
+  const int total = a.batch * H * gw;
+  const bool vec = (W % 4) == 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int b = i / HW, r = i - b * HW;
-    const int py = r / W, px = r - py * W;
-    out[i] = d2d_forward_px(a, lvl, b, py, px, sy, sx);
+    const int g = i % gw, r = i / gw;
+    const int py = r % H, b = r / H;
+    const float* d = a.disp[lvl] + (size_t)b * h * w;
+    const Lerp ty = up_taps(py, h, sy);
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int px = g * 4 + k;
+      if (px < W) {
+        const float up = d2d_up(d, w, ty, up_taps(px, w, sx));
+        v[k] = a.sql ? up : div_(1.0f, add(a.min_disp, mul(a.disp_span, up)));
+      } else {
+        v[k] = 0.0f;
+      }
+    }
+    float* o = out + (size_t)b * HW + py * W + g * 4;
+    if (vec) {
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (g * 4 + k < W) o[k] = v[k];
+    }
   }
 }
 
@@ -451,7 +476,7 @@ int bbd_disp_to_depth_forward(const bbd_d2d_args* a, bbd_stream_t stream) {
   if (a->levels < 1 || a->levels > BBD_MAX_SCALES) return fail(BBD_E_RANGE, "d2d: bad level count");
   for (int l = 0; l < a->levels; ++l)
     if (!a->disp[l] || a->h[l] < 1 || a->w[l] < 1) return fail(BBD_E_ARG, "d2d forward: bad level");
-  const size_t total = (size_t)a->batch * a->height * a->width;
+  const size_t total = (size_t)a->batch * a->height * ((a->width + 3) / 4);
   dim3 grid(grid_for(total, 256), 1, a->levels);
   d2d_forward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
   return check_launch("d2d_forward_kernel");

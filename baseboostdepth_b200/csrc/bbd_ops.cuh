@@ -52,6 +52,40 @@ BBD_HD float d2d_axis_weight(int o, int i, int in_size, float scale) {
   return (t.i0 == i ? t.l0 : 0.0f) + (t.i1 == i ? t.l1 : 0.0f);
 }
 
+// integer factor F known at compile time: the 2F+2 candidate weights per axis live in registers
+template <int F>
+BBD_HD float d2d_backward_gather(const bbd_d2d_args& a, int lvl, int b, int iy, int ix, float sy, float sx) {
+  constexpr int N = 2 * F + 2;
+  const int h = a.h[lvl], w = a.w[lvl], H = a.height, W = a.width;
+  const float* gd = a.gdepth + ((size_t)lvl * a.batch + b) * H * W;
+  const float* dep = a.depth + ((size_t)lvl * a.batch + b) * H * W;
+  const float nspan = -a.disp_span;
+  const int oy0 = iy * F - F / 2 - 1, ox0 = ix * F - F / 2 - 1;
+  float wx[N], wy[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const int ox = ox0 + k, oy = oy0 + k;
+    wx[k] = (ox >= 0 && ox < W) ? d2d_axis_weight(ox, ix, w, sx) : 0.0f;
+    wy[k] = (oy >= 0 && oy < H) ? d2d_axis_weight(oy, iy, h, sy) : 0.0f;
+  }
+  float acc = 0.0f;
+#pragma unroll
+  for (int r = 0; r < N; ++r) {
+    if (wy[r] == 0.0f) continue;
+    const int base = (oy0 + r) * W + ox0;
+    float row = 0.0f;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      if (wx[k] == 0.0f) continue;
+      float v = gd[base + k];
+      if (!a.sql) { const float d = dep[base + k]; v *= nspan * d * d; }
+      row += wx[k] * v;
+    }
+    acc += wy[r] * row;
+  }
+  return acc;
+}
+
 BBD_HD float d2d_backward_px(const bbd_d2d_args& a, int lvl, int b, int iy, int ix, float sy, float sx) {
   const int h = a.h[lvl], w = a.w[lvl], H = a.height, W = a.width;
   const float* gd = a.gdepth + ((size_t)lvl * a.batch + b) * H * W;
@@ -62,6 +96,12 @@ BBD_HD float d2d_backward_px(const bbd_d2d_args& a, int lvl, int b, int iy, int 
     const int o = iy * W + ix;
     acc = gd[o];
     if (!a.sql) acc *= nspan * dep[o] * dep[o];
+  } else if (H == 2 * h && W == 2 * w) {
+    acc = d2d_backward_gather<2>(a, lvl, b, iy, ix, sy, sx);
+  } else if (H == 4 * h && W == 4 * w) {
+    acc = d2d_backward_gather<4>(a, lvl, b, iy, ix, sy, sx);
+  } else if (H == 8 * h && W == 8 * w) {
+    acc = d2d_backward_gather<8>(a, lvl, b, iy, ix, sy, sx);
   } else {
     // src(o) = (o + 0.5)/f - 0.5 lies in (i-1, i+1) for o in [f*i - f/2, f*i + 3f/2 - 1]; one extra
     // output on each side covers the clamped borders and rounding

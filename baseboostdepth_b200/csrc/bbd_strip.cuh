@@ -23,6 +23,9 @@
 #ifndef BBD_UNROLL_BWD
 #define BBD_UNROLL_BWD 1
 #endif
+#ifndef BBD_PACKED_STATS
+#define BBD_PACKED_STATS 1
+#endif
 #define BBD_PRAGMA(x) _Pragma(#x)
 #define BBD_UNROLL(n) BBD_PRAGMA(unroll n)
 
@@ -110,6 +113,26 @@ BBD_HD float w9p(const float* p, const float* q) {
   return s;
 }
 
+// the same sums for two window positions p0 / p1 (and q0 / q1) at once
+BBD_HD f2 ld2(const float* p0, const float* p1, int o) { return mk2(p0[o], p1[o]); }
+BBD_HD f2 w9_2(const float* p0, const float* p1) {
+  f2 s = ld2(p0, p1, 0);
+  s = add(s, ld2(p0, p1, 1)); s = add(s, ld2(p0, p1, 2));
+  s = add(s, ld2(p0, p1, 32)); s = add(s, ld2(p0, p1, 33)); s = add(s, ld2(p0, p1, 34));
+  s = add(s, ld2(p0, p1, 64)); s = add(s, ld2(p0, p1, 65)); s = add(s, ld2(p0, p1, 66));
+  return s;
+}
+// sums of x*x and x*y over the window from one pass over the loads
+BBD_HD void w9pp_2(const float* x0, const float* x1, const float* y0, const float* y1, f2& sxx, f2& sxy, f2& sx) {
+  const int offs[9] = {0, 1, 2, 32, 33, 34, 64, 65, 66};
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const f2 x = ld2(x0, x1, offs[i]), y = ld2(y0, y1, offs[i]);
+    if (i == 0) { sx = x; sxx = mul(x, x); sxy = mul(x, y); }
+    else { sx = add(sx, x); sxx = add(sxx, mul(x, x)); sxy = add(sxy, mul(x, y)); }
+  }
+}
+
 template <class C>
 BBD_HD void rs_load_target(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t, int tid) {
   const int H = a.height, W = a.width, HW = H * W;
@@ -192,8 +215,61 @@ template <class C>
 BBD_HD void rs_stats(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t, int k) {
   const float* pred = sm.pred + (size_t)k * 3 * C::R2N;
   constexpr int ITERS = (C::R1H + C::NW - 1) / C::NW;
+  int m_begin = 0;
+#if BBD_PACKED_STATS
+  // rows i0 = warp and i1 = warp + NW as one packed pair (both exist: R1H >= 2 NW is asserted)
+  if (!a.no_ssim) {
+    static_assert(C::R1H >= 2 * C::NW, "packed statistics need two full row sets");
+    m_begin = 2;
+    const int i0 = t.warp, i1 = t.warp + C::NW;
+    int py0, py1;
+    const bool v0 = rs_center<C>(a, t, i0, py0), v1 = rs_center<C>(a, t, i1, py1);
+    if (v0 || v1) {
+      const int lane = (t.lane < 1) ? 1 : t.lane;  // keep the window inside the plane for idle lanes
+      const int o0 = i0 * C::P + lane - 1, o1 = i1 * C::P + lane - 1;
+      const int j0 = i0 * C::P + t.lane, j1 = i1 * C::P + t.lane;
+      f2 ssim_sum = bc2(0.0f), l1_sum = bc2(0.0f);
+      f2 wsx[3], wsxx[3], wsxy[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* x = pred + c * C::R2N;
+        const float* y = sm.tgt + c * C::R2N;
+        const f2 d = sub(ld2(y + o0, y + o1, C::P + 1), ld2(x + o0, x + o1, C::P + 1));
+        const f2 l1 = mk2(fabsf(d.x), fabsf(d.y));
+        l1_sum = (c == 0) ? l1 : add(l1_sum, l1);
+        w9pp_2(x + o0, x + o1, y + o0, y + o1, wsxx[c], wsxy[c], wsx[c]);
+        const f2 muy = mk2(sm.tst[(2 * c) * C::R1N + j0], sm.tst[(2 * c) * C::R1N + j1]);
+        const f2 sigy = mk2(sm.tst[(2 * c + 1) * C::R1N + j0], sm.tst[(2 * c + 1) * C::R1N + j1]);
+        const f2 v = ssim_channel2(wsx[c], wsxx[c], wsxy[c], muy, sigy);
+        ssim_sum = (c == 0) ? v : add(ssim_sum, v);
+      }
+      // 0.85 * mean_c(ssim) + 0.15 * mean_c(l1), packed (same order as photometric_mix)
+      const f2 loss = add(mul(bc2(BBD_W_SSIM), mul(ssim_sum, bc2(BBD_THIRD))), mul(bc2(BBD_W_L1), mul(l1_sum, bc2(BBD_THIRD))));
+      if (v0 && (k == 0 || loss.x < sm.best[j0])) {
+        sm.best[j0] = loss.x;
+        sm.bidx[j0] = k;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          sm.stash[(3 * c) * C::R1N + j0] = wsx[c].x;
+          sm.stash[(3 * c + 1) * C::R1N + j0] = wsxx[c].x;
+          sm.stash[(3 * c + 2) * C::R1N + j0] = wsxy[c].x;
+        }
+      }
+      if (v1 && (k == 0 || loss.y < sm.best[j1])) {
+        sm.best[j1] = loss.y;
+        sm.bidx[j1] = k;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          sm.stash[(3 * c) * C::R1N + j1] = wsx[c].y;
+          sm.stash[(3 * c + 1) * C::R1N + j1] = wsxx[c].y;
+          sm.stash[(3 * c + 2) * C::R1N + j1] = wsxy[c].y;
+        }
+      }
+    }
+  }
+#endif
   BBD_UNROLL(BBD_UNROLL_STATS)
-  for (int m = 0; m < ITERS; ++m) {
+  for (int m = m_begin; m < ITERS; ++m) {
     const int i = t.warp + m * C::NW;
     if (i >= C::R1H) break;
     int py;

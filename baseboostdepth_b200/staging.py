@@ -8,9 +8,30 @@ the previous batch is still being consumed; the compute stream only waits on an 
 """
 from __future__ import annotations
 
+import os
 from typing import Dict
 
 import torch
+
+
+def bind_to_gpu_numa(device_index: int) -> str:
+    """Pin this process to the CPU cores next to the GPU (NVML affinity) *before* allocating pinned
+    memory, so the staging arena is NUMA-local to the GPU's PCIe root.  Returns a short description;
+    does nothing (and says so) when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [i * 64 + b for i, wd in enumerate(mask) for b in range(64) if (wd >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return "no overlap between NVML affinity and the allowed CPUs"
+        os.sched_setaffinity(0, allowed)
+        return f"bound to {len(allowed)} cores next to GPU {device_index}"
+    except Exception as exc:  # noqa: BLE001
+        return f"not bound ({type(exc).__name__})"
 
 
 class BatchStager:
