@@ -22,6 +22,9 @@ namespace bbd {
 #ifndef BBD_MIN_BLOCKS
 #define BBD_MIN_BLOCKS 3
 #endif
+#ifndef BBD_SEP_BWD
+#define BBD_SEP_BWD 1
+#endif
 #ifndef BBD_WARPS
 #define BBD_WARPS 8
 #endif
@@ -100,11 +103,13 @@ __device__ __forceinline__ void block_reduce(float* red, int tid, const float* v
 // grid (tiles_x, tiles_y, S*B): one block per tile of one (scale, sample).  (Walking over the four
 // scales inside one block to share the target tile was measured slower: 4x fewer blocks, more
 // live state -> spills at 80 registers.)
-template <bool GRAD>
+// KEEP: one warped tile per candidate stays in shared memory (fastest for <= 2 candidates);
+// otherwise a single tile buffer is reused and the backward recomputes the warped value.
+template <bool GRAD, bool KEEP>
 __global__ void __launch_bounds__(SCfg::NT, BBD_MIN_BLOCKS) reproj_kernel(const bbd_reproj_args a) {
   extern __shared__ float smem[];
   StripSmem<SCfg> sm;
-  sm.carve(smem, a.max_rep);
+  sm.carve(smem, KEEP ? a.max_rep : 1);
   const int tid = threadIdx.x;
   const StripCtx t = make_strip<SCfg>(blockIdx.x, blockIdx.y, blockIdx.z, tid, a.batch, a.height, a.width);
   const int n_rep = a.tab.hdr[(size_t)t.b * 4];
@@ -115,9 +120,10 @@ __global__ void __launch_bounds__(SCfg::NT, BBD_MIN_BLOCKS) reproj_kernel(const 
   rs_target_stats<SCfg>(a, sm, t);
   {
     for (int k = 0; k < n_rep; ++k) {
-      rs_warp<SCfg>(a, sm, t, k);
+      if (!KEEP && k) __syncthreads();  // the single warped-tile buffer is reused by every candidate
+      rs_warp<SCfg, KEEP>(a, sm, t, k);
       __syncthreads();
-      rs_stats<SCfg>(a, sm, t, k);
+      rs_stats<SCfg, KEEP>(a, sm, t, k);
     }
     const float part = rs_select<SCfg>(a, sm, t, n_rep);
     block_reduce<1>(sm.red, tid, &part, a.loss_part + ((size_t)t.s * a.batch + t.b) * t.ntiles + t.tile);
@@ -130,7 +136,23 @@ __global__ void __launch_bounds__(SCfg::NT, BBD_MIN_BLOCKS) reproj_kernel(const 
           continue;
         }
         float gP[12];
-        rs_backward<SCfg>(a, sm, t, k, gP);
+#if BBD_SEP_BWD
+        {
+          const float* src;
+          Cam cam;
+          rs_candidate(a, t.b, k, src, cam);
+#pragma unroll
+          for (int i = 0; i < 12; ++i) gP[i] = 0.0f;
+          for (int q = t.warp; q < SCfg::TH; q += SCfg::NW) {  // warp-uniform
+            rs_bwd_vertical<SCfg>(a, sm, t, k, q);
+            __syncwarp();
+            rs_bwd_horizontal<SCfg, KEEP>(a, sm, t, k, q, src, cam, gP);
+            __syncwarp();
+          }
+        }
+#else
+        rs_backward<SCfg>(a, sm, t, k, gP);  // A/B reference; recomputes the warped value
+#endif
         block_reduce<12>(sm.red, tid, gP, out);
       }
       rs_store_gdepth<SCfg>(a, sm, t);
@@ -422,15 +444,19 @@ int bbd_reproj_fused(const bbd_reproj_args* a, bbd_stream_t stream) {
   if (a->need_grad && (!a->gpose_part || !a->gdepth)) return fail(BBD_E_ARG, "reproj: gradient buffers missing");
   if (a->batch <= 0 || a->height < 2 || a->width < 2 || a->num_scales <= 0) return fail(BBD_E_ARG, "reproj: bad size");
   if (a->max_rep < 1 || a->max_rep > BBD_MAX_REP) return fail(BBD_E_RANGE, "reproj: max_rep out of range");
-  const size_t smem = StripSmem<SCfg>::floats(a->max_rep) * sizeof(float);
+  // keep every candidate's warped tile resident while that still allows three blocks per SM
+  const bool keep = StripSmem<SCfg>::floats(a->max_rep) * sizeof(float) <= 75 * 1024;
+  const size_t smem = StripSmem<SCfg>::floats(keep ? a->max_rep : 1) * sizeof(float);
   if (smem > 227 * 1024) return fail(BBD_E_RANGE, "reproj: shared memory budget exceeded");
   dim3 grid((a->width + SCfg::TW - 1) / SCfg::TW, (a->height + SCfg::TH - 1) / SCfg::TH, a->num_scales * a->batch);
+  auto launch = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, SCfg::NT, smem, (cudaStream_t)stream>>>(*a);
+  };
   if (a->need_grad) {
-    cudaFuncSetAttribute(reproj_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    reproj_kernel<true><<<grid, SCfg::NT, smem, (cudaStream_t)stream>>>(*a);
+    if (keep) launch(reproj_kernel<true, true>); else launch(reproj_kernel<true, false>);
   } else {
-    cudaFuncSetAttribute(reproj_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    reproj_kernel<false><<<grid, SCfg::NT, smem, (cudaStream_t)stream>>>(*a);
+    if (keep) launch(reproj_kernel<false, true>); else launch(reproj_kernel<false, false>);
   }
   return check_launch("reproj_kernel");
 }

@@ -44,7 +44,7 @@ struct StripCfg {
 template <class C>
 struct StripSmem {
   float* tgt;    // [3][R2N]
-  float* pred;   // [max_rep][3][R2N]
+  float* pred;   // [npred][3][R2N]  warped tiles: one per candidate (KEEP) or a single reused buffer
   float* tst;    // [6][R1N]  target window mean / variance term per channel
   float* stash;  // [9][R1N]  window sums of the best candidate -> gradient coefficients
   float* best;   // [R1N]
@@ -52,13 +52,13 @@ struct StripSmem {
   float* gd;     // [INN]
   float* red;    // [NW][12] warp partials of the block reduction (the CPU harness brings its own scratch)
   int* anywin;   // [BBD_MAX_REP]
-  static constexpr size_t floats(int max_rep) {
-    return 3 * C::R2N + (size_t)max_rep * 3 * C::R2N + 6 * C::R1N + 9 * C::R1N + 2 * C::R1N + C::INN + C::NW * 12 +
+  static constexpr size_t floats(int npred) {
+    return 3 * C::R2N + (size_t)npred * 3 * C::R2N + 6 * C::R1N + 9 * C::R1N + 2 * C::R1N + C::INN + C::NW * 12 +
            BBD_MAX_REP;
   }
-  BBD_HD void carve(float* base, int max_rep) {
+  BBD_HD void carve(float* base, int npred) {
     tgt = base; base += 3 * C::R2N;
-    pred = base; base += (size_t)max_rep * 3 * C::R2N;
+    pred = base; base += (size_t)npred * 3 * C::R2N;
     tst = base; base += 6 * C::R1N;
     stash = base; base += 9 * C::R1N;
     best = base; base += C::R1N;
@@ -186,14 +186,14 @@ BBD_HD void rs_candidate(const bbd_reproj_args& a, int b, int k, const float*& s
   load_cam(cam, a.inv_K + (size_t)e[3] * 16, a.P + (size_t)e[2] * 12, a.width, a.height);
 }
 
-template <class C>
+template <class C, bool KEEP>
 BBD_HD void rs_warp(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t, int k) {
   const int H = a.height, W = a.width, HW = H * W;
   const float* src;
   Cam cam;
   rs_candidate(a, t.b, k, src, cam);
   const float* depth = a.depth + ((size_t)t.s * a.batch + t.b) * HW;
-  float* pred = sm.pred + (size_t)k * 3 * C::R2N;
+  float* pred = sm.pred + (KEEP ? (size_t)k * 3 * C::R2N : 0);
   constexpr int ITERS = (C::R2H + C::NW - 1) / C::NW;
   BBD_UNROLL(BBD_UNROLL_WARP)
   for (int m = 0; m < ITERS; ++m) {
@@ -211,9 +211,9 @@ BBD_HD void rs_warp(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& 
   }
 }
 
-template <class C>
+template <class C, bool KEEP>
 BBD_HD void rs_stats(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t, int k) {
-  const float* pred = sm.pred + (size_t)k * 3 * C::R2N;
+  const float* pred = sm.pred + (KEEP ? (size_t)k * 3 * C::R2N : 0);
   constexpr int ITERS = (C::R1H + C::NW - 1) / C::NW;
   int m_begin = 0;
 #if BBD_PACKED_STATS
@@ -379,7 +379,6 @@ BBD_HD void rs_backward(const bbd_reproj_args& a, StripSmem<C>& sm, const StripC
   Cam cam;
   rs_candidate(a, t.b, k, src, cam);
   const float* depth = a.depth + ((size_t)t.s * a.batch + t.b) * HW;
-  const float* pred = sm.pred + (size_t)k * 3 * C::R2N;
 #pragma unroll
   for (int i = 0; i < 12; ++i) gP[i] = 0.0f;
   const bool lane_ok = t.lane >= 2 && t.lane <= 29 && t.u < W;
@@ -415,28 +414,104 @@ BBD_HD void rs_backward(const bbd_reproj_args& a, StripSmem<C>& sm, const StripC
     if (!any) continue;
     const int ctr2 = (q + 2) * C::P + t.lane;
     const bool own = sm.bidx[(q + 1) * C::P + t.lane] == k;
-    float gpred[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float x = pred[c * C::R2N + ctr2], y = sm.tgt[c * C::R2N + ctr2];
-      float g = sa[c] + sb[c] * x + sc[c] * y;
-      if (own) {
-        const float d = sub(y, x);  // l1 = |target - pred|; abs'(0) = 0
-        g += (d > 0.0f) ? -g_l1 : ((d < 0.0f) ? g_l1 : 0.0f);
-      }
-      gpred[c] = g;
-    }
     Sample s;
     project_pixel(cam, t.px, py, depth[py * W + t.px], W, H, s);
     Taps tp;
     make_taps(s, W, H, tp);
     float gix = 0.0f, giy = 0.0f;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) tap_channel_grad(src + c * HW, s, tp, gpred[c], gix, giy);
+    for (int c = 0; c < 3; ++c) {
+      const float* plane = src + c * HW;
+      const float x = tap_channel(plane, tp), y = sm.tgt[c * C::R2N + ctr2];
+      float g = sa[c] + sb[c] * x + sc[c] * y;
+      if (own) {
+        const float d = sub(y, x);  // l1 = |target - pred|; abs'(0) = 0
+        g += (d > 0.0f) ? -g_l1 : ((d < 0.0f) ? g_l1 : 0.0f);
+      }
+      tap_channel_grad(plane, s, tp, g, gix, giy);
+    }
     float gdep = 0.0f;
     chain_to_depth_pose(cam, s, gix, giy, gdep, gP);
     sm.gd[q * C::P + t.lane] += gdep;
   }
+}
+
+// ---- separable form of the backward gather ------------------------------------------------
+// The 3x3 masked sum of the coefficient planes is done as a vertical pass (every lane sums the
+// three window centres of its own column) followed by a horizontal pass over the neighbouring
+// lanes.  The exchange buffer is warp-private ([10][32] floats per warp, carved out of the target
+// statistics planes, which are dead once the winners are selected), so the two passes are
+// separated by a warp barrier only.
+template <class C>
+BBD_HD float* rs_xch(StripSmem<C>& sm, const StripCtx& t) { return sm.tst + t.warp * 320; }
+
+template <class C>
+BBD_HD void rs_bwd_vertical(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t, int k, int q) {
+  static_assert(C::NW * 320 <= 6 * C::R1N, "exchange buffers must fit the target statistics planes");
+  const int py = t.y0 + q;
+  if (py >= a.height || t.lane < 1 || t.lane > 30) return;
+  float* x = rs_xch<C>(sm, t);
+  const float my0 = (py == 1) ? 2.0f : 1.0f, my2 = (py == a.height - 2) ? 2.0f : 1.0f;
+  float v[9];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) v[e] = 0.0f;
+  bool any = false;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int j = (q + dy) * C::P + t.lane;  // R1 row q+dy = window centre row q+1 + (dy-1)
+    if (sm.bidx[j] != k) continue;
+    any = true;
+    const float my = dy == 0 ? my0 : (dy == 2 ? my2 : 1.0f);
+#pragma unroll
+    for (int e = 0; e < 9; ++e) v[e] += my * sm.stash[e * C::R1N + j];
+  }
+#pragma unroll
+  for (int e = 0; e < 9; ++e) x[e * 32 + t.lane] = v[e];
+  x[9 * 32 + t.lane] = any ? 1.0f : 0.0f;
+}
+
+template <class C, bool KEEP>
+BBD_HD void rs_bwd_horizontal(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t, int k, int q,
+                              const float* src, const Cam& cam, float gP[12]) {
+  const int H = a.height, W = a.width, HW = H * W;
+  const int py = t.y0 + q;
+  if (py >= H || t.lane < 2 || t.lane > 29 || t.u >= W) return;
+  const float* x = rs_xch<C>(sm, t);
+  if (x[9 * 32 + t.lane - 1] + x[9 * 32 + t.lane] + x[9 * 32 + t.lane + 1] == 0.0f) return;
+  const float wgt = 1.0f / ((float)a.batch * (float)H * (float)W);
+  const float g_l1 = a.no_ssim ? wgt * BBD_THIRD : wgt * BBD_W_L1 * BBD_THIRD;
+  // multiplicity of a neighbouring window: a reflected border pixel sits twice in it
+  const float mx0 = (t.u == 1) ? 2.0f : 1.0f, mx2 = (t.u == W - 2) ? 2.0f : 1.0f;
+  const int ctr2 = (q + 2) * C::P + t.lane;
+  const bool own = sm.bidx[(q + 1) * C::P + t.lane] == k;
+  // KEEP: every candidate's warped tile is still in shared memory.  Otherwise the warped value of
+  // this pixel is recomputed from the four taps the gradient needs anyway (bit-identical to
+  // rs_warp), so shared memory does not grow with the number of candidates (tri-min / decomp).
+  const float* depth = a.depth + ((size_t)t.s * a.batch + t.b) * HW;
+  Sample s;
+  project_pixel(cam, t.px, py, depth[py * W + t.px], W, H, s);
+  Taps tp;
+  make_taps(s, W, H, tp);
+  float gix = 0.0f, giy = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* xa = x + (3 * c) * 32 + t.lane;
+    const float sa = mx0 * xa[-1] + xa[0] + mx2 * xa[1];
+    const float sb = mx0 * xa[31] + xa[32] + mx2 * xa[33];
+    const float sc = mx0 * xa[63] + xa[64] + mx2 * xa[65];
+    const float* plane = src + c * HW;
+    const float xv = KEEP ? sm.pred[((size_t)k * 3 + c) * C::R2N + ctr2] : tap_channel(plane, tp);
+    const float yv = sm.tgt[c * C::R2N + ctr2];
+    float g = sa + sb * xv + sc * yv;
+    if (own) {
+      const float d = sub(yv, xv);  // l1 = |target - pred|; abs'(0) = 0
+      g += (d > 0.0f) ? -g_l1 : ((d < 0.0f) ? g_l1 : 0.0f);
+    }
+    tap_channel_grad(plane, s, tp, g, gix, giy);
+  }
+  float gdep = 0.0f;
+  chain_to_depth_pose(cam, s, gix, giy, gdep, gP);
+  sm.gd[q * C::P + t.lane] += gdep;
 }
 
 template <class C>

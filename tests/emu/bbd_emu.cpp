@@ -74,7 +74,10 @@ int emu_ident_forward(const bbd_ident_args* ap) {
 
 int emu_reproj_fused(const bbd_reproj_args* ap) {
   const bbd_reproj_args& a = *ap;
-  std::vector<float> smem(StripSmem<SCfg>::floats(a.max_rep));
+  // the CPU harness runs the reuse (non-KEEP) variant for batches with more than two candidates,
+  // like the launcher does
+  const bool keep = StripSmem<SCfg>::floats(a.max_rep) * sizeof(float) <= 75 * 1024;
+  std::vector<float> smem(StripSmem<SCfg>::floats(keep ? a.max_rep : 1));
   std::vector<float> red(12 * SCfg::NT + 12 * SCfg::RED_SEG * 2);  // host-side reduction scratch
   std::vector<float> gPs((size_t)SCfg::NT * 12), parts(SCfg::NT);
   std::vector<StripCtx> ctx(SCfg::NT);
@@ -83,7 +86,7 @@ int emu_reproj_fused(const bbd_reproj_args* ap) {
     for (int by = 0; by < gy; ++by)
       for (int bx = 0; bx < gx; ++bx) {
         StripSmem<SCfg> sm;
-        sm.carve(smem.data(), a.max_rep);
+        sm.carve(smem.data(), keep ? a.max_rep : 1);
         sm.red = red.data();
         FOR_STID ctx[tid] = make_strip<SCfg>(bx, by, bz, tid, a.batch, a.height, a.width);
         const int b = ctx[0].b, tile = ctx[0].tile, ntiles = ctx[0].ntiles;
@@ -94,8 +97,13 @@ int emu_reproj_fused(const bbd_reproj_args* ap) {
           const int s = ctx[0].s;
           FOR_STID rs_begin_scale<SCfg>(sm, tid);
           for (int k = 0; k < n_rep; ++k) {
-            FOR_STID rs_warp<SCfg>(a, sm, ctx[tid], k);
-            FOR_STID rs_stats<SCfg>(a, sm, ctx[tid], k);
+            if (keep) {
+              FOR_STID rs_warp<SCfg, true>(a, sm, ctx[tid], k);
+              FOR_STID rs_stats<SCfg, true>(a, sm, ctx[tid], k);
+            } else {
+              FOR_STID rs_warp<SCfg, false>(a, sm, ctx[tid], k);
+              FOR_STID rs_stats<SCfg, false>(a, sm, ctx[tid], k);
+            }
           }
           FOR_STID parts[tid] = rs_select<SCfg>(a, sm, ctx[tid], n_rep);
           FOR_STID rs_park<SCfg, 1>(sm.red, tid, &parts[tid]);
@@ -108,10 +116,17 @@ int emu_reproj_fused(const bbd_reproj_args* ap) {
               for (int i = 0; i < 12; ++i) out[i] = 0.0f;
               continue;
             }
-            FOR_STID {
-              rs_backward<SCfg>(a, sm, ctx[tid], k, &gPs[(size_t)tid * 12]);
-              rs_park<SCfg, 12>(sm.red, tid, &gPs[(size_t)tid * 12]);
+            {
+              const float* src;
+              Cam cam;
+              rs_candidate(a, b, k, src, cam);
+              for (size_t i = 0; i < gPs.size(); ++i) gPs[i] = 0.0f;
+              for (int m = 0; m * SCfg::NW < SCfg::TH; ++m) {   // one row per warp at a time, lanes in lockstep
+                FOR_STID { const int q = ctx[tid].warp + m * SCfg::NW; if (q < SCfg::TH) rs_bwd_vertical<SCfg>(a, sm, ctx[tid], k, q); }
+                FOR_STID { const int q = ctx[tid].warp + m * SCfg::NW; if (q < SCfg::TH) { if (keep) rs_bwd_horizontal<SCfg, true>(a, sm, ctx[tid], k, q, src, cam, &gPs[(size_t)tid * 12]); else rs_bwd_horizontal<SCfg, false>(a, sm, ctx[tid], k, q, src, cam, &gPs[(size_t)tid * 12]); } }
+              }
             }
+            FOR_STID rs_park<SCfg, 12>(sm.red, tid, &gPs[(size_t)tid * 12]);
             FOR_STID rs_level1<SCfg, 12>(sm.red, tid);
             FOR_STID rs_level2<SCfg, 12>(sm.red, tid, out);
           }
