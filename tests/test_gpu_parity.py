@@ -205,3 +205,20 @@ def test_tier_a_operators_on_gpu(cuda_device):
     assert rel_l2(d_g.grad, d_c.grad) <= 1e-5 and rel_l2(x_g.grad, x_c.grad) <= 2e-5
     norm = torch.rand(n, 1, H, W, generator=gen)
     assert abs(float(L.get_smooth_loss(norm.to(dev), x.to(dev))) - float(O.smooth_loss(norm, x))) <= 1e-6
+
+
+def test_batch_stager_roundtrip(cuda_device):
+    """staging.BatchStager: one pinned arena, one DMA per batch, double-buffered."""
+    from baseboostdepth_b200.staging import BatchStager
+    gen = torch.Generator().manual_seed(1)
+    template = {("a", 0): torch.rand(3, 5, 7, generator=gen), "b": torch.rand(11, generator=gen), "meta": [1, 2]}
+    st = BatchStager(template, cuda_device)
+    assert st.nbytes >= (3 * 5 * 7 + 11) * 4
+    for it in range(4):                                  # more iterations than slots
+        st.host["b"].fill_(float(it))
+        slot = st.upload_async()
+        v = st.views(slot)
+        assert torch.equal(v[("a", 0)].cpu(), template[("a", 0)])
+        assert float(v["b"][0]) == float(it)
+        st.release(slot)
+    torch.cuda.synchronize()
