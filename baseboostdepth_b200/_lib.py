@@ -50,14 +50,14 @@ class D2DArgs(C.Structure):
                 ("h", C.c_int32 * MAX_SCALES), ("w", C.c_int32 * MAX_SCALES), ("min_disp", C.c_float),
                 ("disp_span", C.c_float), ("sql", C.c_int32), ("disp", fp * MAX_SCALES), ("depth", fp),
                 ("gdepth", fp), ("gscale", fp), ("gsmooth", fp * MAX_SCALES), ("gsmooth_scale", fp),
-                ("gdisp", fp * MAX_SCALES)]
+                ("gdisp", fp * MAX_SCALES), ("scratch", fp)]
 
 
 # every symbol include/bbd_loss.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "bbd_version", "bbd_last_error_string", "bbd_reproj_tiles", "bbd_ident_forward", "bbd_reproj_fused",
     "bbd_reproj_finalize", "bbd_warp_forward", "bbd_smooth_scratch_floats", "bbd_smooth_fused",
-    "bbd_disp_to_depth_forward", "bbd_disp_to_depth_backward", "bbd_backproject_forward",
+    "bbd_disp_to_depth_forward", "bbd_disp_to_depth_backward", "bbd_d2d_scratch_floats", "bbd_backproject_forward",
     "bbd_backproject_backward", "bbd_project_forward", "bbd_project_chunks", "bbd_project_backward",
     "bbd_ssim_forward", "bbd_ssim_backward", "bbd_pose_pack_forward", "bbd_pose_pack_backward",
     "bbd_pose_forward", "bbd_pose_backward",
@@ -88,6 +88,7 @@ class Backend:
         for name in ("reproj_tiles", "project_chunks"):
             getattr(self.dll, prefix + name).restype = C.c_int
         getattr(self.dll, prefix + "smooth_scratch_floats").restype = C.c_size_t
+        getattr(self.dll, prefix + "d2d_scratch_floats").restype = C.c_size_t
         if cuda:
             self.dll.bbd_last_error_string.restype = C.c_char_p
 
@@ -108,7 +109,7 @@ class Backend:
         if self.cuda:
             args = args + (self.stream(),)
         rc = fn(*args)
-        self.launches += 3 if name == "smooth_fused" else 1
+        self.launches += {"smooth_fused": 3, "disp_to_depth_backward": 2}.get(name, 1)
         if rc != 0:
             msg = self.dll.bbd_last_error_string().decode() if self.cuda else ""
             raise RuntimeError(f"bbd_{name} failed with code {rc}: {msg}")

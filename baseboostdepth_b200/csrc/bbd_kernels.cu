@@ -4,6 +4,8 @@
 // (see baseboostdepth_b200/build.py).  No torch types cross this file's boundary.
 #include <cuda_runtime.h>
 #include <stdio.h>
+
+#include <algorithm>
 #include <string.h>
 
 #include "bbd_ops.cuh"
@@ -305,6 +307,22 @@ __global__ void __launch_bounds__(256) d2d_forward_kernel(const bbd_d2d_args a) 
   }
 }
 
+// pass 1 of the separable disparity-gradient gather: row sums (B,H,w) per level upsampled by 2/4/8
+__global__ void __launch_bounds__(256) d2d_hpass_kernel(const bbd_d2d_args a) {
+  const int lvl = blockIdx.z;
+  const int f = d2d_sep_factor(a, lvl);
+  if (!f) return;
+  const int w = a.w[lvl], H = a.height;
+  const float sx = div_((float)w, (float)a.width);
+  float* tmp = a.scratch + d2d_scratch_offset(a, lvl);
+  const int total = a.batch * H * w;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ix = i % w, r = i / w;
+    const int oy = r % H, b = r / H;
+    tmp[i] = f == 2 ? d2d_hpass<2>(a, lvl, b, oy, ix, sx) : (f == 4 ? d2d_hpass<4>(a, lvl, b, oy, ix, sx) : d2d_hpass<8>(a, lvl, b, oy, ix, sx));
+  }
+}
+
 __global__ void __launch_bounds__(128) d2d_backward_kernel(const bbd_d2d_args a) {
   const int lvl = blockIdx.z;
   const int h = a.h[lvl], w = a.w[lvl], hw = h * w;
@@ -519,9 +537,21 @@ int bbd_disp_to_depth_backward(const bbd_d2d_args* a, bbd_stream_t stream) {
     const size_t n = (size_t)a->batch * a->h[l] * a->w[l];
     if (n > most) most = n;
   }
+  if (a->scratch) {
+    size_t rows = 1;
+    for (int l = 0; l < a->levels; ++l)
+      if (d2d_sep_factor(*a, l)) rows = std::max(rows, (size_t)a->batch * a->height * a->w[l]);
+    dim3 hgrid(grid_for(rows, 256), 1, a->levels);
+    d2d_hpass_kernel<<<hgrid, 256, 0, (cudaStream_t)stream>>>(*a);
+  }
   dim3 grid(grid_for(most, 128), 1, a->levels);
   d2d_backward_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*a);
   return check_launch("d2d_backward_kernel");
+}
+
+size_t bbd_d2d_scratch_floats(const bbd_d2d_args* a) {
+  if (!a) return 0;
+  return d2d_scratch_offset(*a, a->levels);
 }
 
 int bbd_pose_forward(int32_t n, const float* axisangle, const float* translation, int32_t invert, float* T,

@@ -52,6 +52,63 @@ BBD_HD float d2d_axis_weight(int o, int i, int in_size, float scale) {
   return (t.i0 == i ? t.l0 : 0.0f) + (t.i1 == i ? t.l1 : 0.0f);
 }
 
+// ---- separable gather for the factors 2, 4, 8 ------------------------------------------------
+// factor of a level if the two-pass path applies to it, else 0
+BBD_HD int d2d_sep_factor(const bbd_d2d_args& a, int lvl) {
+  const int h = a.h[lvl], w = a.w[lvl];
+  for (int f = 2; f <= 8; f *= 2)
+    if (a.height == f * h && a.width == f * w) return f;
+  return 0;
+}
+// offset (floats) of level lvl's row-sum plane (B,H,w) inside the scratch buffer
+BBD_HD size_t d2d_scratch_offset(const bbd_d2d_args& a, int lvl) {
+  size_t off = 0;
+  for (int l = 0; l < lvl; ++l)
+    if (d2d_sep_factor(a, l)) off += (size_t)a.batch * a.height * a.w[l];
+  return off;
+}
+// pass 1: for one full-resolution row oy and one low-resolution column ix, the weighted sum over
+// the 2F+2 outputs that can have ix as a tap (chain rule of disp_to_depth applied on the fly)
+template <int F>
+BBD_HD float d2d_hpass(const bbd_d2d_args& a, int lvl, int b, int oy, int ix, float sx) {
+  constexpr int N = 2 * F + 2;
+  const int w = a.w[lvl], H = a.height, W = a.width;
+  const size_t plane = ((size_t)lvl * a.batch + b) * H * W + (size_t)oy * W;
+  const float* gd = a.gdepth + plane;
+  const float* dep = a.depth + plane;
+  const float nspan = -a.disp_span;
+  const int ox0 = ix * F - F / 2 - 1;
+  float acc = 0.0f;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const int ox = ox0 + k;
+    if (ox < 0 || ox >= W) continue;
+    const float wx = d2d_axis_weight(ox, ix, w, sx);
+    if (wx == 0.0f) continue;
+    float v = gd[ox];
+    if (!a.sql) { const float d = dep[ox]; v *= nspan * d * d; }
+    acc += wx * v;
+  }
+  return acc;
+}
+// pass 2: weighted sum of the row sums over the 2F+2 rows that can have iy as a tap
+template <int F>
+BBD_HD float d2d_vpass(const bbd_d2d_args& a, int lvl, int b, int iy, int ix, float sy) {
+  constexpr int N = 2 * F + 2;
+  const int h = a.h[lvl], w = a.w[lvl], H = a.height;
+  const float* tmp = a.scratch + d2d_scratch_offset(a, lvl) + (size_t)b * H * w;
+  const int oy0 = iy * F - F / 2 - 1;
+  float acc = 0.0f;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const int oy = oy0 + k;
+    if (oy < 0 || oy >= H) continue;
+    const float wy = d2d_axis_weight(oy, iy, h, sy);
+    if (wy != 0.0f) acc += wy * tmp[(size_t)oy * w + ix];
+  }
+  return acc;
+}
+
 // integer factor F known at compile time: the 2F+2 candidate weights per axis live in registers
 template <int F>
 BBD_HD float d2d_backward_gather(const bbd_d2d_args& a, int lvl, int b, int iy, int ix, float sy, float sx) {
@@ -96,12 +153,12 @@ BBD_HD float d2d_backward_px(const bbd_d2d_args& a, int lvl, int b, int iy, int 
     const int o = iy * W + ix;
     acc = gd[o];
     if (!a.sql) acc *= nspan * dep[o] * dep[o];
-  } else if (H == 2 * h && W == 2 * w) {
-    acc = d2d_backward_gather<2>(a, lvl, b, iy, ix, sy, sx);
-  } else if (H == 4 * h && W == 4 * w) {
-    acc = d2d_backward_gather<4>(a, lvl, b, iy, ix, sy, sx);
-  } else if (H == 8 * h && W == 8 * w) {
-    acc = d2d_backward_gather<8>(a, lvl, b, iy, ix, sy, sx);
+  } else if (a.scratch && H == 2 * h && W == 2 * w) {
+    acc = d2d_vpass<2>(a, lvl, b, iy, ix, sy);
+  } else if (a.scratch && H == 4 * h && W == 4 * w) {
+    acc = d2d_vpass<4>(a, lvl, b, iy, ix, sy);
+  } else if (a.scratch && H == 8 * h && W == 8 * w) {
+    acc = d2d_vpass<8>(a, lvl, b, iy, ix, sy);
   } else {
     // src(o) = (o + 0.5)/f - 0.5 lies in (i-1, i+1) for o in [f*i - f/2, f*i + 3f/2 - 1]; one extra
     // output on each side covers the clamped borders and rounding

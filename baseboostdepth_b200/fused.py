@@ -183,6 +183,9 @@ class _FusedLoss(torch.autograd.Function):
         for l, g in enumerate(gdisps):
             d2d.gdisp[l] = g.data_ptr()
             d2d.gsmooth[l] = gsm[l].data_ptr()
+        scratch = torch.empty(max(1, be.value("d2d_scratch_floats", C.byref(d2d))), device=gdepth.device,
+                              dtype=torch.float32)
+        d2d.scratch = scratch.data_ptr()
         be.call("disp_to_depth_backward", C.byref(d2d))
         return (None, gP) + tuple(gdisps)
 

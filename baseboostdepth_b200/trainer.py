@@ -184,6 +184,7 @@ class FusedLossMixin:
 
     collect_ident = False     # fill self.ident like trainer.py:547 (costs an argmin plane write)
     always_warp = False       # materialise ("color", f, s) every step, not only when logging
+    _bbd_backend = None       # tests point this at the CPU harness; None = the CUDA library
 
     def _bbd_plan(self, inputs) -> LossPlan:
         s_rows = inputs[("color", "s", 0)].shape[0] if ("color", "s", 0) in inputs else None
@@ -203,12 +204,13 @@ class FusedLossMixin:
         plan = getattr(self, "_bbd_current_plan", None) or self._bbd_plan(inputs)
         want = bool(self.collect_ident and self.opt.trimin)
         losses = loss_step(inputs, outputs, self.opt, plan, num_scales=self.num_scales, want_winner=want,
-                           row_masks=self._bbd_row_masks())
+                           row_masks=self._bbd_row_masks(), backend=self._bbd_backend)
         if want:
             self.ident = ident_statistics(plan, outputs["argmin"][-1])
         if self.always_warp or getattr(self, "early_phase", 1) == 0:
             with torch.no_grad():
-                materialise_warps(inputs, outputs, self.opt, plan, row_masks=self._bbd_row_masks())
+                materialise_warps(inputs, outputs, self.opt, plan, row_masks=self._bbd_row_masks(),
+                                  backend=self._bbd_backend)
         return losses
 
 

@@ -222,8 +222,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     from baseboostdepth_b200.staging import bind_to_gpu_numa
-    numa = bind_to_gpu_numa(int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local])
-                            if os.environ.get("CUDA_VISIBLE_DEVICES") else local)
+    try:   # NVML indexes physical devices; CUDA_VISIBLE_DEVICES may remap (or hold UUIDs)
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        numa = bind_to_gpu_numa(int(vis.split(",")[local]) if vis else local)
+    except (ValueError, IndexError):
+        numa = "not bound (CUDA_VISIBLE_DEVICES is not a list of indices)" 
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -264,7 +267,9 @@ def run_ours(args):
 
     def step():
         rebuild_poses()
-        losses = loss_step(inputs, outputs, opt, plan, noise=noise, num_scales=4, timers=timers)
+        # noise=None: the tie-break noise is drawn on the device inside the step, one torch.randn per
+        # baseline group, exactly like compute_losses does (trainer.py:518-523)
+        losses = loss_step(inputs, outputs, opt, plan, noise=None, num_scales=4, timers=timers)
         losses["loss"].backward()
         return losses["loss"]
 
@@ -296,7 +301,7 @@ def run_ours(args):
     kern_ms = sum(a.elapsed_time(b) for a, b in kernel_ev if a is not None) / max(1, len(kernel_ev))
 
     # ---- end to end: pinned host batch -> H2D -> fused loss fwd+bwd -> D2H loss ---------------
-    # Every step uploads its whole batch (images, pyramid, K, noise, disparities, camera motions)
+    # Every step uploads its whole batch (images, pyramid, K, stereo_T, disparities, camera motions)
     # from pinned host memory; BatchStager moves it as one DMA on a side stream, double-buffered,
     # so step i+1's upload overlaps step i's kernels.  The loss value is read back every step.
     e2e = None
@@ -304,21 +309,18 @@ def run_ours(args):
         from baseboostdepth_b200.staging import BatchStager
         template = {("in",) + (k if isinstance(k, tuple) else (k,)): v for k, v in inputs.items() if torch.is_tensor(v)}
         template.update({("leaf",) + k: v for k, v in leaves.items() if k[0] in ("disp", "cam_T_cam")})
-        template.update({("noise", g): n for g, n in noise.items()})
         stager = BatchStager(template, dev)
         h2d = stager.nbytes
 
         def consume(slot):
             v = stager.views(slot)
             gin = {"ordering": inputs["ordering"]}
-            gout, gnoise = {}, {}
+            gout = {}
             for k, t in v.items():
                 if k[0] == "in":
                     gin[k[1] if len(k) == 2 else k[1:]] = t
-                elif k[0] == "leaf":
-                    gout[k[1:]] = t.detach().requires_grad_(True)
                 else:
-                    gnoise[k[1]] = t
+                    gout[k[1:]] = t.detach().requires_grad_(True)
             for k in outputs:
                 if k[0] == "cam_T_cam" and k not in gout:
                     gout[k] = outputs[k]
@@ -326,7 +328,7 @@ def run_ours(args):
                     te = gout[k].detach().clone()
                     te[:, :3, 3:] /= 5.5
                     gout[("cam_T_cam_error", 0, k[2])] = te
-            losses = loss_step(gin, gout, opt, plan, noise=gnoise, num_scales=4)
+            losses = loss_step(gin, gout, opt, plan, noise=None, num_scales=4)   # noise drawn on the device
             losses["loss"].backward()
             stager.release(slot)
             return losses["loss"].detach()

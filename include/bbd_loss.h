@@ -178,7 +178,10 @@ typedef struct bbd_d2d_args {
   const float* gsmooth[BBD_MAX_SCALES]; /* (B,1,h,w) optional extra term (smoothness gradient), or NULL */
   const float* gsmooth_scale;        /* (S) device: gdisp += gsmooth_scale[s] * gsmooth[s] */
   float* gdisp[BBD_MAX_SCALES];      /* (B,1,h,w) backward only */
+  float* scratch;                    /* backward only: bbd_d2d_scratch_floats() floats (row sums of the
+                                        separable gather for the levels upsampled by 2, 4 or 8) */
 } bbd_d2d_args;
+size_t bbd_d2d_scratch_floats(const bbd_d2d_args* a);
 int bbd_disp_to_depth_forward(const bbd_d2d_args* a, bbd_stream_t stream);
 int bbd_disp_to_depth_backward(const bbd_d2d_args* a, bbd_stream_t stream);
 

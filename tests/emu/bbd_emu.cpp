@@ -234,8 +234,22 @@ int emu_disp_to_depth_forward(const bbd_d2d_args* ap) {
   return 0;
 }
 
+size_t emu_d2d_scratch_floats(const bbd_d2d_args* a) { return d2d_scratch_offset(*a, a->levels); }
+
 int emu_disp_to_depth_backward(const bbd_d2d_args* ap) {
   const bbd_d2d_args& a = *ap;
+  if (a.scratch)
+    for (int lvl = 0; lvl < a.levels; ++lvl) {
+      const int f = d2d_sep_factor(a, lvl);
+      if (!f) continue;
+      const int w = a.w[lvl], H = a.height;
+      const float sx = (float)w / (float)a.width;
+      float* tmp = a.scratch + d2d_scratch_offset(a, lvl);
+      for (int i = 0; i < a.batch * H * w; ++i) {
+        const int ix = i % w, r = i / w, oy = r % H, b = r / H;
+        tmp[i] = f == 2 ? d2d_hpass<2>(a, lvl, b, oy, ix, sx) : (f == 4 ? d2d_hpass<4>(a, lvl, b, oy, ix, sx) : d2d_hpass<8>(a, lvl, b, oy, ix, sx));
+      }
+    }
   for (int lvl = 0; lvl < a.levels; ++lvl) {
     const int h = a.h[lvl], w = a.w[lvl];
     const float sy = (float)h / (float)a.height, sx = (float)w / (float)a.width;
