@@ -366,6 +366,18 @@ __global__ void warp_kernel(int n, int H, int W, const float* images, const floa
   }
 }
 
+__global__ void grid_sample_kernel(int n, int C, int H, int W, int HoWo, const float* images, const float* grid, float* out) {
+  const size_t total = (size_t)n * HoWo;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    grid_sample_px(C, H, W, HoWo, images, grid, (int)(i / HoWo), (int)(i % HoWo), out);
+}
+__global__ void grid_sample_grad_kernel(int n, int C, int H, int W, int HoWo, const float* images, const float* grid,
+                                        const float* gout, float* ggrid) {
+  const size_t total = (size_t)n * HoWo;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    grid_sample_grad_px(C, H, W, HoWo, images, grid, gout, (int)(i / HoWo), (int)(i % HoWo), ggrid);
+}
+
 __global__ void backproject_kernel(int n, int H, int W, const float* depth, const float* inv_K, float* points) {
   const int HW = H * W;
   const size_t total = (size_t)n * HW;
@@ -632,6 +644,25 @@ int bbd_project_backward(int32_t n, int32_t height, int32_t width, const float* 
   dim3 grid(bbd_project_chunks(height, width), n);
   project_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, height, width, points, P, eps, gpix, gpoints, gP_part);
   return check_launch("project_grad_kernel");
+}
+
+int bbd_grid_sample_forward(int32_t n, int32_t channels, int32_t height, int32_t width, int32_t out_h, int32_t out_w,
+                            const float* images, const float* grid, float* out, bbd_stream_t stream) {
+  if (!images || !grid || !out) return fail(BBD_E_ARG, "grid_sample: null argument");
+  if (n * channels == 0 || out_h * out_w == 0) return 0;
+  grid_sample_kernel<<<grid_for((size_t)n * out_h * out_w, 256), 256, 0, (cudaStream_t)stream>>>(
+      n, channels, height, width, out_h * out_w, images, grid, out);
+  return check_launch("grid_sample_kernel");
+}
+
+int bbd_grid_sample_backward(int32_t n, int32_t channels, int32_t height, int32_t width, int32_t out_h, int32_t out_w,
+                             const float* images, const float* grid, const float* gout, float* ggrid,
+                             bbd_stream_t stream) {
+  if (!images || !grid || !gout || !ggrid) return fail(BBD_E_ARG, "grid_sample backward: null argument");
+  if (n == 0 || out_h * out_w == 0) return 0;
+  grid_sample_grad_kernel<<<grid_for((size_t)n * out_h * out_w, 256), 256, 0, (cudaStream_t)stream>>>(
+      n, channels, height, width, out_h * out_w, images, grid, gout, ggrid);
+  return check_launch("grid_sample_grad_kernel");
 }
 
 int bbd_ssim_forward(int32_t n, int32_t channels, int32_t height, int32_t width, const float* x, const float* y, float* out,

@@ -312,6 +312,39 @@ BBD_HD void warp_px(int H, int W, const float* images, const float* depth, const
   }
 }
 
+// ---- F.grid_sample(bilinear, border, align_corners=True) as a standalone operator ------------
+// coordinate part of ATen's grid_sampler for one axis: unnormalise + clip (+ gradient mask)
+BBD_HD float gs_coord(float g, int size, float& mask) {
+  const float lim = (float)(size - 1);
+  float v = mul(mul(add(g, 1.0f), 0.5f), lim);
+  if (!(v > 0.0f)) { v = 0.0f; mask = 0.0f; } else if (v >= lim) { v = lim; mask = 0.0f; } else { mask = 1.0f; }
+  return v;
+}
+BBD_HD void gs_sample(int H, int W, float gx, float gy, Sample& s, Taps& t) {
+  s.ix = gs_coord(gx, W, s.mx);
+  s.iy = gs_coord(gy, H, s.my);
+  s.x0 = (int)floorf(s.ix);
+  s.y0 = (int)floorf(s.iy);
+  make_taps(s, W, H, t);
+}
+BBD_HD void grid_sample_px(int C, int H, int W, int HoWo, const float* images, const float* grid, int n, int o, float* out) {
+  Sample s; Taps t;
+  gs_sample(H, W, grid[((size_t)n * 2) * HoWo + o], grid[((size_t)n * 2 + 1) * HoWo + o], s, t);
+  for (int c = 0; c < C; ++c)
+    out[((size_t)n * C + c) * HoWo + o] = tap_channel(images + ((size_t)n * C + c) * H * W, t);
+}
+BBD_HD void grid_sample_grad_px(int C, int H, int W, int HoWo, const float* images, const float* grid, const float* gout,
+                                int n, int o, float* ggrid) {
+  Sample s; Taps t;
+  gs_sample(H, W, grid[((size_t)n * 2) * HoWo + o], grid[((size_t)n * 2 + 1) * HoWo + o], s, t);
+  float gix = 0.0f, giy = 0.0f;
+  for (int c = 0; c < C; ++c)
+    tap_channel_grad(images + ((size_t)n * C + c) * H * W, s, t, gout[((size_t)n * C + c) * HoWo + o], gix, giy);
+  // d ix / d gx = (W-1)/2 (align_corners), times the clip mask
+  ggrid[((size_t)n * 2) * HoWo + o] = gix * s.mx * (0.5f * (float)(W - 1));
+  ggrid[((size_t)n * 2 + 1) * HoWo + o] = giy * s.my * (0.5f * (float)(H - 1));
+}
+
 // ---- BackprojectDepth (layers.py:160-167) --------------------------------------------------
 BBD_HD void backproject_px(int HW, int W, const float* depth, const float* inv_K, int n, int i, float* points) {
   const float* ik = inv_K + (size_t)n * 16;

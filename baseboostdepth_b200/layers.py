@@ -234,3 +234,42 @@ def get_smooth_loss(disp, img):
     if img.requires_grad:
         raise NotImplementedError("bbd get_smooth_loss: gradient w.r.t. the image is not provided")
     return _Smooth.apply(disp, img)
+
+
+class _GridSample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, images, grid):
+        be = _backend()
+        img = images.detach().contiguous()
+        g = grid.detach().permute(0, 3, 1, 2).contiguous()     # (n,2,Ho,Wo): no copy for Project3D's output
+        be.check_device(img, g)
+        n, c, h, w = img.shape
+        ho, wo = g.shape[2], g.shape[3]
+        out = torch.empty(n, c, ho, wo, device=img.device, dtype=torch.float32)
+        be.call("grid_sample_forward", n, c, h, w, ho, wo, _p(img), _p(g), _p(out))
+        ctx.save_for_backward(img, g)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("bbd grid_sample: gradient w.r.t. the sampled image is not provided "
+                                      "(the trainer never requests it)")
+        be = _backend()
+        img, g = ctx.saved_tensors
+        n, c, h, w = img.shape
+        ho, wo = g.shape[2], g.shape[3]
+        go = gout.contiguous()
+        gg = torch.empty_like(g)
+        be.call("grid_sample_backward", n, c, h, w, ho, wo, _p(img), _p(g), _p(go), _p(gg))
+        return None, gg.permute(0, 2, 3, 1)
+
+
+def grid_sample(images, grid, align_corners=True, padding_mode="border", mode="bilinear"):
+    """``F.grid_sample`` for the one configuration the trainer uses (``trainer.py:439,442``):
+    bilinear, border padding, ``align_corners=True``.  Gradient flows to ``grid`` only.
+    ``torch.nn.functional.grid_sample = baseboostdepth_b200.layers.grid_sample`` lets an unchanged
+    ``trainer.py`` use it (tier A)."""
+    if not (align_corners and padding_mode == "border" and mode == "bilinear"):
+        raise NotImplementedError("bbd grid_sample implements bilinear / border / align_corners=True only")
+    return _GridSample.apply(images, grid)

@@ -201,6 +201,16 @@ int bbd_project_chunks(int32_t height, int32_t width);
 int bbd_project_backward(int32_t n, int32_t height, int32_t width, const float* points, const float* P,
                          float eps, const float* gpix, float* gpoints, float* gP_part,
                          bbd_stream_t stream);
+/* trainer.py:442 / :439: F.grid_sample(images, grid, align_corners=True, padding_mode="border"),
+ * bilinear.  images (n,C,H,W); grid laid out (n,2,Ho,Wo) -- the permuted memory Project3D returns;
+ * out (n,C,Ho,Wo).  backward: gradient w.r.t. the grid only (per-pixel gather, deterministic); the
+ * source-image gradient (a bilinear splat) is never requested by the trainer and is not provided. */
+int bbd_grid_sample_forward(int32_t n, int32_t channels, int32_t height, int32_t width, int32_t out_h,
+                            int32_t out_w, const float* images, const float* grid, float* out,
+                            bbd_stream_t stream);
+int bbd_grid_sample_backward(int32_t n, int32_t channels, int32_t height, int32_t width, int32_t out_h,
+                             int32_t out_w, const float* images, const float* grid, const float* gout,
+                             float* ggrid /* (n,2,Ho,Wo) */, bbd_stream_t stream);
 /* layers.py:235-249; gx / gy may be NULL */
 int bbd_ssim_forward(int32_t n, int32_t channels, int32_t height, int32_t width, const float* x,
                      const float* y, float* out, bbd_stream_t stream);

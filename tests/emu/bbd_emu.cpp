@@ -312,6 +312,19 @@ int emu_project_backward(int32_t n, int32_t H, int32_t W, const float* points, c
   }
   return 0;
 }
+int emu_grid_sample_forward(int32_t n, int32_t C, int32_t H, int32_t W, int32_t Ho, int32_t Wo, const float* images,
+                            const float* grid, float* out) {
+  for (int b = 0; b < n; ++b)
+    for (int o = 0; o < Ho * Wo; ++o) grid_sample_px(C, H, W, Ho * Wo, images, grid, b, o, out);
+  return 0;
+}
+int emu_grid_sample_backward(int32_t n, int32_t C, int32_t H, int32_t W, int32_t Ho, int32_t Wo, const float* images,
+                             const float* grid, const float* gout, float* ggrid) {
+  for (int b = 0; b < n; ++b)
+    for (int o = 0; o < Ho * Wo; ++o) grid_sample_grad_px(C, H, W, Ho * Wo, images, grid, gout, b, o, ggrid);
+  return 0;
+}
+
 int emu_ssim_forward(int32_t n, int32_t ch, int32_t H, int32_t W, const float* x, const float* y, float* out) {
   for (size_t pl = 0; pl < (size_t)n * ch; ++pl)
     for (int i = 0; i < H * W; ++i) out[pl * H * W + i] = ssim_px(x + pl * H * W, y + pl * H * W, H, W, i / W, i % W);

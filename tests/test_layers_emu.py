@@ -158,11 +158,15 @@ def test_reference_trainer_runs_unchanged_on_drop_in_layers():
         tr.valid_frames_trimin(g.inputs)
         real_randn, drawn = torch.randn, iter([g.noise[k] / 0.00001 for k in [f for f in tr.valid_frames if f == "s" or f > 0]])
         torch.randn = lambda *a, **k: next(drawn)
+        import torch.nn.functional as F
+        real_gs = F.grid_sample
+        F.grid_sample = L.grid_sample                      # trainer.py:439,442 call F.grid_sample directly
         try:
             tr.generate_images_pred(g.inputs, g.outputs)
             losses = tr.compute_losses(g.inputs, g.outputs)
         finally:
             torch.randn = real_randn
+            F.grid_sample = real_gs
         assert abs(float(losses["loss"]) - g.losses["loss"]) <= 2e-6
         losses["loss"].backward()
         for k, ref in g.grads.items():
@@ -192,3 +196,21 @@ def test_pose_kernel_matches_tensor_version(invert):
     assert rel_l2(res[1][1][1:], res[0][1][1:]) <= 1e-5
     assert rel_l2(res[1][2], res[0][2]) <= 1e-5
     assert torch.isfinite(res[1][1]).all()
+
+
+def test_grid_sample_matches_aten():
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(21)
+    img = torch.rand(2, 3, 10, 14, generator=gen)
+    base = torch.rand(2, 2, 6, 9, generator=gen) * 2.6 - 1.3          # some coordinates outside [-1, 1]
+    base[0, 0, 0, 0], base[0, 1, 0, 1] = -1.0, 1.0                   # exactly on the border
+    w = torch.rand(2, 3, 6, 9, generator=gen)
+    res = []
+    for fn in (lambda i, g: F.grid_sample(i, g, align_corners=True, padding_mode="border"), L.grid_sample):
+        raw = base.clone().requires_grad_(True)
+        grid = raw.permute(0, 2, 3, 1)                               # the non-contiguous view Project3D returns
+        out = fn(img, grid)
+        (out * w).sum().backward()
+        res.append((out.detach(), raw.grad))
+    assert max_abs(res[1][0], res[0][0]) <= 1e-6
+    assert max_abs(res[1][1], res[0][1]) <= 1e-5
