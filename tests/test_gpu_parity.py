@@ -222,3 +222,20 @@ def test_batch_stager_roundtrip(cuda_device):
         assert float(v["b"][0]) == float(it)
         st.release(slot)
     torch.cuda.synchronize()
+
+
+def test_grid_sample_on_gpu(cuda_device):
+    import torch.nn.functional as F
+    import baseboostdepth_b200.layers as L
+    gen = torch.Generator().manual_seed(31)
+    img = torch.rand(3, 3, 48, 80, generator=gen).to(cuda_device)
+    base = (torch.rand(3, 2, 48, 80, generator=gen) * 2.4 - 1.2).to(cuda_device)
+    w = torch.rand(3, 3, 48, 80, generator=gen).to(cuda_device)
+    res = []
+    for fn in (lambda i, g: F.grid_sample(i, g, align_corners=True, padding_mode="border"), L.grid_sample):
+        raw = base.clone().requires_grad_(True)
+        out = fn(img, raw.permute(0, 2, 3, 1))
+        (out * w).sum().backward()
+        res.append((out.detach(), raw.grad))
+    assert max_abs(res[1][0], res[0][0]) <= 1e-6
+    assert max_abs(res[1][1], res[0][1]) <= 2e-5
