@@ -55,8 +55,8 @@ def _frame_poses(plan: LossPlan, inputs, outputs, key="cam_T_cam", row_masks=Non
         if f == "s":
             if key != "cam_T_cam":
                 continue
-            idx = torch.as_tensor(plan.sel["s"], device=inputs["stereo_T"].device, dtype=torch.long)
-            T[f] = inputs["stereo_T"].index_select(0, idx)
+            T[f] = inputs["stereo_T"].index_select(0, _index_tensor(plan, ("sel", "s"), plan.sel["s"],
+                                                                   inputs["stereo_T"].device))
             continue
         Tf = outputs[(key, 0, f)]
         n = len(plan.sel[f])
@@ -68,6 +68,18 @@ def _frame_poses(plan: LossPlan, inputs, outputs, key="cam_T_cam", row_masks=Non
             Tf = Tf[row_masks[abs(f)]]
         T[f] = Tf
     return T
+
+
+def _index_tensor(plan: LossPlan, key, values, device):
+    """Small index tensors derived from the plan, uploaded once (keeps steps free of H2D copies so
+    that a step can be captured in a CUDA graph)."""
+    cache = plan.__dict__.setdefault("_index_cache", {})
+    k = (key, str(device))
+    t = cache.get(k)
+    if t is None:
+        t = torch.as_tensor(list(values), device=device, dtype=torch.long)
+        cache[k] = t
+    return t
 
 
 def draw_noise(plan: LossPlan, height, width, device):
@@ -157,8 +169,8 @@ def materialise_warps(inputs, outputs, opt, plan: LossPlan, scales=None, backend
         depth = outputs[("depth", 0, s)].detach()
         for f in plan.frames:
             n = len(plan.sel[f])
-            rows = torch.as_tensor(plan.stack_row[f], device=color0.device, dtype=torch.long)
-            sel = torch.as_tensor(plan.sel[f], device=color0.device, dtype=torch.long)
+            rows = _index_tensor(plan, ("rows", f), plan.stack_row[f], color0.device)
+            sel = _index_tensor(plan, ("sel", f), plan.sel[f], color0.device)
             images = inputs[("color", f, 0)].index_select(0, rows).contiguous()
             d = depth.index_select(0, sel).contiguous()
             for key, poses in (("color", T), ("color_D", T_err)):

@@ -89,3 +89,26 @@ def test_forward_only_mode():
         losses, _ = run_fused(g.inputs, g.outputs, g.opt(), g.noise, g.num_scales, backend=emu_backend())
     assert abs(float(losses["loss"]) - g.losses["loss"]) <= 2e-6
     assert not losses["loss"].requires_grad
+
+
+def test_sql_mode_emulated():
+    """opt.SQL (disp is depth, trainer.py:457-458) through the kernels' phase code on the CPU."""
+    from baseboostdepth_b200.synthetic import make_batch, make_noise
+    from baseboostdepth_b200.trainer import plan_for
+    cfg = dict(batch=2, height=32, width=64, baselines=[1, 1], trimin=False, decomp=False)
+    opt = O.default_opt(height=32, width=64, scales=[0], SQL=True, batch_size=2)
+    res = []
+    for mine in (False, True):
+        inputs, outputs, params = make_batch(seed=12, device="cpu", scales=(0,), **cfg)
+        with torch.no_grad():
+            params[("disp", 0)].mul_(20.0).add_(1.0)
+        plan = plan_for(inputs["ordering"], False, False, None)
+        noise = make_noise(plan, 32, 64, seed=3)
+        if mine:
+            losses, _ = run_fused(inputs, outputs, opt, noise, 4, backend=emu_backend())
+        else:
+            losses, _ = O.run(inputs, outputs, opt, noise, num_scales=4)
+        losses["loss"].backward()
+        res.append((float(losses["loss"]), params[("disp", 0)].grad.clone()))
+    assert abs(res[0][0] - res[1][0]) <= 2e-6
+    assert rel_l2(res[1][1], res[0][1]) <= 1e-5

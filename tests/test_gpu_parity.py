@@ -239,3 +239,71 @@ def test_grid_sample_on_gpu(cuda_device):
         res.append((out.detach(), raw.grad))
     assert max_abs(res[1][0], res[0][0]) <= 1e-6
     assert max_abs(res[1][1], res[0][1]) <= 2e-5
+
+
+def test_step_is_cuda_graph_capturable(cuda_device):
+    """include/bbd_loss.h promises graph-capturable entry points: capture loss_step + backward once,
+    replay it on new input values, compare with an eager evaluation."""
+    from baseboostdepth_b200.trainer import loss_step
+    cfg = dict(batch=3, height=64, width=96, baselines=[2, 1, "s"], trimin=True, decomp=False)
+    opt = O.default_opt(height=64, width=96, trimin=True, batch_size=3)
+    gi, go, gp = make_batch(seed=8, device=cuda_device, **cfg)
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in go.items()
+              if k[0] in ("disp", "cam_T_cam") and v.numel()}
+    static_out = {k: leaves.get(k, v) for k, v in go.items()}
+    plan = plan_for(gi["ordering"], True, False, gi[("color", "s", 0)].shape[0])
+    noise = {k: v.to(cuda_device) for k, v in make_noise(plan, 64, 96, seed=2).items()}
+
+    def run():
+        for p in leaves.values():
+            p.grad = None
+        losses = loss_step(gi, dict(static_out), opt, plan, noise=noise, num_scales=4)
+        losses["loss"].backward()
+        return losses["loss"]
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            run()                                  # warm-up: caches tables, weights, allocator pools
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    for p in leaves.values():
+        p.grad = None
+    with torch.cuda.graph(graph):
+        loss_static = loss_step(gi, dict(static_out), opt, plan, noise=noise, num_scales=4)["loss"]
+        loss_static.backward()
+    grads_static = {k: p.grad for k, p in leaves.items()}
+
+    # new values in the same buffers, replay, compare with eager
+    with torch.no_grad():
+        leaves[("disp", 0)].mul_(0.5).add_(0.02)
+        gi[("color", 1, 0)].mul_(0.9)
+    graph.replay()
+    torch.cuda.synchronize()
+    got_loss = float(loss_static)
+    got = {k: g.clone() for k, g in grads_static.items()}
+    want_loss = float(run())
+    torch.cuda.synchronize()
+    assert got_loss == want_loss
+    for k, p in leaves.items():
+        assert torch.equal(got[k], p.grad), k
+
+
+def test_sql_mode_matches_oracle(cuda_device):
+    """opt.SQL: the network output is depth itself (trainer.py:457-458); single scale like the reference uses."""
+    cfg = dict(batch=2, height=64, width=96, baselines=[1, 1], trimin=False, decomp=False)
+    opt = O.default_opt(height=64, width=96, scales=[0], SQL=True, batch_size=2)
+    inputs, outputs, params = make_batch(seed=12, device="cpu", scales=(0,), **cfg)
+    with torch.no_grad():
+        params[("disp", 0)].mul_(20.0).add_(1.0)          # depth-like magnitudes
+    plan = plan_for(inputs["ordering"], False, False, None)
+    noise = make_noise(plan, 64, 96, seed=3)
+    retain_pose_grads(outputs)
+    ref, aux = O.run(inputs, outputs, opt, noise, num_scales=4)
+    ref["loss"].backward()
+    gi, go, leaves = mirror_to_device(inputs, outputs, params, cuda_device)
+    losses, _ = run_fused(gi, go, opt, {k: v.to(cuda_device) for k, v in noise.items()}, 4, groups=aux["groups"])
+    losses["loss"].backward()
+    assert abs(float(losses["loss"]) - float(ref["loss"])) <= 2e-6
+    assert rel_l2(leaves[("disp", 0)].grad, params[("disp", 0)].grad) <= 1e-5
