@@ -300,6 +300,36 @@ def run_ours(args):
     step_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
     kern_ms = sum(a.elapsed_time(b) for a, b in kernel_ev if a is not None) / max(1, len(kernel_ev))
 
+    # ---- the same step captured once in a CUDA graph and replayed (no Python / launch overhead) ----
+    graph_ms = None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    for p in leaves.values():
+                        p.grad = None
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            for p in leaves.values():
+                p.grad = None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step()
+            gev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            barrier()
+            for i in range(args.steps):
+                flush.zero_()
+                gev[i][0].record()
+                g.replay()
+                gev[i][1].record()
+            barrier()
+            graph_ms = sum(a.elapsed_time(b) for a, b in gev) / args.steps
+        except Exception as exc:  # noqa: BLE001
+            graph_ms = None
+            print(f"graph capture failed: {type(exc).__name__}: {exc}", file=sys.stderr)
+
     # ---- end to end: pinned host batch -> H2D -> fused loss fwd+bwd -> D2H loss ---------------
     # Every step uploads its whole batch (images, pyramid, K, stereo_T, disparities, camera motions)
     # from pinned host memory; BatchStager moves it as one DMA on a side stream, double-buffered,
@@ -367,10 +397,11 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- max over ranks ------------------------------------------------------------------------
-    vals = torch.tensor([step_ms, kern_ms, e2e_ms or 0.0, wall * 1e3 / args.steps], device=dev, dtype=torch.float64)
+    vals = torch.tensor([step_ms, kern_ms, e2e_ms or 0.0, wall * 1e3 / args.steps, graph_ms or 0.0], device=dev,
+                        dtype=torch.float64)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    step_ms, kern_ms, e2e_ms_max, wall_ms = (float(v) for v in vals.cpu())
+    step_ms, kern_ms, e2e_ms_max, wall_ms, graph_ms_max = (float(v) for v in vals.cpu())
 
     if rank == 0:
         peaks = {}
@@ -394,7 +425,8 @@ def run_ours(args):
                        "scales": 4, "px_pairs_per_step_per_gpu": pairs, "sharding": f"batch x{world}, no data-path collective",
                        "l2": "flushed between steps (256 MiB memset, outside the per-step events)",
                        "timing": "CUDA events per step on the launch stream, mean over steps, max over ranks",
-                       "wall_ms_per_step_incl_flush": wall_ms},
+                       "wall_ms_per_step_incl_flush": wall_ms,
+                       "cuda_graph_replay_ms_per_step": graph_ms_max if graph_ms is not None else None},
             "roofline": {"bound": "hbm", "kernel": "reproj_kernel<true>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "kernel_ms": kern_ms,
