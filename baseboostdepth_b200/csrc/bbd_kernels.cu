@@ -24,9 +24,6 @@ namespace bbd {
 #ifndef BBD_MIN_BLOCKS
 #define BBD_MIN_BLOCKS 3
 #endif
-#ifndef BBD_SEP_BWD
-#define BBD_SEP_BWD 1
-#endif
 #ifndef BBD_WARPS
 #define BBD_WARPS 8
 #endif
@@ -138,7 +135,6 @@ __global__ void __launch_bounds__(SCfg::NT, BBD_MIN_BLOCKS) reproj_kernel(const 
           continue;
         }
         float gP[12];
-#if BBD_SEP_BWD
         {
           const float* src;
           Cam cam;
@@ -152,9 +148,6 @@ __global__ void __launch_bounds__(SCfg::NT, BBD_MIN_BLOCKS) reproj_kernel(const 
             __syncwarp();
           }
         }
-#else
-        rs_backward<SCfg>(a, sm, t, k, gP);  // A/B reference; recomputes the warped value
-#endif
         block_reduce<12>(sm.red, tid, gP, out);
       }
       rs_store_gdepth<SCfg>(a, sm, t);

@@ -20,9 +20,6 @@
 #ifndef BBD_UNROLL_STATS
 #define BBD_UNROLL_STATS 1
 #endif
-#ifndef BBD_UNROLL_BWD
-#define BBD_UNROLL_BWD 1
-#endif
 #ifndef BBD_PACKED_STATS
 #define BBD_PACKED_STATS 1
 #endif
@@ -368,72 +365,6 @@ BBD_HD float rs_select(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCt
     sm.bidx[j] = win;
   }
   return part;
-}
-
-template <class C>
-BBD_HD void rs_backward(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t, int k, float gP[12]) {
-  const int H = a.height, W = a.width, HW = H * W;
-  const float wgt = 1.0f / ((float)a.batch * (float)H * (float)W);
-  const float g_l1 = a.no_ssim ? wgt * BBD_THIRD : wgt * BBD_W_L1 * BBD_THIRD;
-  const float* src;
-  Cam cam;
-  rs_candidate(a, t.b, k, src, cam);
-  const float* depth = a.depth + ((size_t)t.s * a.batch + t.b) * HW;
-#pragma unroll
-  for (int i = 0; i < 12; ++i) gP[i] = 0.0f;
-  const bool lane_ok = t.lane >= 2 && t.lane <= 29 && t.u < W;
-  // multiplicity of a neighbouring window: a reflected border pixel sits twice in it
-  const float mx0 = (t.u == 1) ? 2.0f : 1.0f, mx2 = (t.u == W - 2) ? 2.0f : 1.0f;
-  constexpr int ITERS = (C::TH + C::NW - 1) / C::NW;
-  BBD_UNROLL(BBD_UNROLL_BWD)
-  for (int m = 0; m < ITERS; ++m) {
-    const int q = t.warp + m * C::NW;
-    if (q >= C::TH) break;
-    const int py = t.y0 + q;
-    if (!lane_ok || py >= H) continue;
-    const float my0 = (py == 1) ? 2.0f : 1.0f, my2 = (py == H - 2) ? 2.0f : 1.0f;
-    float sa[3] = {0, 0, 0}, sb[3] = {0, 0, 0}, sc[3] = {0, 0, 0};
-    bool any = false;
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      const float my = dy == 0 ? my0 : (dy == 2 ? my2 : 1.0f);
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int j = (q + dy) * C::P + t.lane + dx - 1;  // R1 row q+dy = centre row q+1 + (dy-1)
-        if (sm.bidx[j] != k) continue;
-        any = true;
-        const float m = my * (dx == 0 ? mx0 : (dx == 2 ? mx2 : 1.0f));
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          sa[c] += m * sm.stash[(3 * c) * C::R1N + j];
-          sb[c] += m * sm.stash[(3 * c + 1) * C::R1N + j];
-          sc[c] += m * sm.stash[(3 * c + 2) * C::R1N + j];
-        }
-      }
-    }
-    if (!any) continue;
-    const int ctr2 = (q + 2) * C::P + t.lane;
-    const bool own = sm.bidx[(q + 1) * C::P + t.lane] == k;
-    Sample s;
-    project_pixel(cam, t.px, py, depth[py * W + t.px], W, H, s);
-    Taps tp;
-    make_taps(s, W, H, tp);
-    float gix = 0.0f, giy = 0.0f;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float* plane = src + c * HW;
-      const float x = tap_channel(plane, tp), y = sm.tgt[c * C::R2N + ctr2];
-      float g = sa[c] + sb[c] * x + sc[c] * y;
-      if (own) {
-        const float d = sub(y, x);  // l1 = |target - pred|; abs'(0) = 0
-        g += (d > 0.0f) ? -g_l1 : ((d < 0.0f) ? g_l1 : 0.0f);
-      }
-      tap_channel_grad(plane, s, tp, g, gix, giy);
-    }
-    float gdep = 0.0f;
-    chain_to_depth_pose(cam, s, gix, giy, gdep, gP);
-    sm.gd[q * C::P + t.lane] += gdep;
-  }
 }
 
 // ---- separable form of the backward gather ------------------------------------------------
