@@ -49,6 +49,15 @@ CASES = {
                         scales=[0], H=32, W=64, seed=16),
     "stress_oob": dict(baselines=[1, 1], trimin=False, decomp=False, no_ssim=False,
                        scales=[0, 3], H=32, W=64, seed=17, stress=True),
+    # ragged geometry: rows not a multiple of the 16-row tile, columns not a multiple of 28
+    "ragged_40x72": dict(baselines=[2, 1, "s"], trimin=True, decomp=False, no_ssim=False,
+                         scales=[0, 1, 2, 3], H=40, W=72, seed=18),
+    # a frame narrower than one tile, a single sample
+    "small_16x24_b1": dict(baselines=[1], trimin=False, decomp=False, no_ssim=False,
+                           scales=[0, 1, 2], H=16, W=24, seed=19),
+    # decomp on a ragged frame, out-of-bounds motion
+    "ragged_decomp_24x40": dict(baselines=[1, 2], trimin=True, decomp=True, no_ssim=False,
+                                scales=[0, 1], H=24, W=40, seed=20, stress=True),
 }
 
 

@@ -12,7 +12,7 @@ import torch
 
 from baseboostdepth_b200.trainer import materialise_warps
 from fused_util import emu_backend, run_fused
-from helpers import Golden, golden_cases, max_abs, rel_l2
+from helpers import Golden, assert_grad_parity, golden_cases, max_abs, rel_l2
 from oracle import loss_path as O
 
 CASES = golden_cases()
@@ -32,8 +32,16 @@ def test_fused_matches_oracle(case):
         assert abs(float(losses[k]) - float(v)) <= 2e-6 * max(1.0, abs(float(v))), k
         assert abs(float(losses[k]) - g.losses[k]) <= 2e-6, k   # and the reference's own number
     losses["loss"].backward()
+    ref64 = None
     for k, gr in ref_grads.items():
-        assert rel_l2(h.params[k].grad, gr) <= 1e-5, (k, rel_l2(h.params[k].grad, gr))
+        if rel_l2(h.params[k].grad, gr) > 1e-5 and ref64 is None:
+            # a few hundred pixels with one ill-conditioned SSIM window: fp32 rounding noise of the
+            # reference itself exceeds the bar -- fall back to the float64 yardstick (helpers.py)
+            d = Golden(case, dtype=torch.float64)
+            l64, _ = O.run(d.inputs, d.outputs, d.opt(), d.noise, num_scales=d.num_scales)
+            l64["loss"].backward()
+            ref64 = {kk: v.grad for kk, v in d.params.items() if v.grad is not None}
+        assert_grad_parity(h.params[k].grad, gr, None if ref64 is None else ref64[k], k)
 
     # depth planes and the per-pixel selection
     for i, s in enumerate(h.scales):

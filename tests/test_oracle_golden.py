@@ -15,7 +15,7 @@ CASES = golden_cases()
 
 
 def test_fixtures_present():
-    assert len(CASES) >= 7
+    assert len(CASES) >= 10
 
 
 @pytest.mark.parametrize("case", CASES)
