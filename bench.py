@@ -455,10 +455,118 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
 
+# ----------------------------------------------------------------------------------------------
+FULL_STEP = {"full_step_640x192_b12": (12, 192, 640), "full_step_1024x320_b8": (8, 320, 1024)}
+
+
+def run_full_step(args):
+    """BASELINE.json configs[4]: encoder/decoder + pose nets + fused loss + Adam, batch-sharded, NCCL
+    all-reduce of the network gradients (scripts/full_step.py).  Secondary line, not the headline."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import full_step as FS
+    from baseboostdepth_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B, H, W = FULL_STEP[args.workload]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    be = _lib.cuda_backend()
+    host = {k: (v.pin_memory() if torch.is_tensor(v) else v)
+            for k, v in FS.make_inputs(B, H, W, "cpu", seed=1234 + rank).items()}
+    inputs = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(trainer, steps, warmup, upload=False):
+        for _ in range(warmup):
+            trainer.step(inputs)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        last = None
+        for _ in range(steps):
+            if upload:
+                batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
+                last = float(trainer.step(batch)["loss"])
+            else:
+                last = trainer.step(inputs)["loss"]
+        ev1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) / steps * 1e3
+        ms = ev0.elapsed_time(ev1) / steps
+        t = torch.tensor([ms, wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), float(last)
+
+    warm = max(3, args.warmup)
+    torch.manual_seed(1)
+    fused = FS.StepTrainer(B, H, W, dev, loss="fused", ddp=world > 1, local_rank=local)
+    sampler.mark()
+    timed(fused, 2, warm)
+    be.launches = 0
+    ms, _, loss = timed(fused, args.steps, 0)
+    launches = be.launches
+    _, e2e_wall, _ = timed(fused, max(10, min(args.steps, 30)), 2, upload=True)
+    clocks = sampler.stop() if rank == 0 else None
+    legs = {}
+    for name in ("none", "eager"):          # context legs on the same GPU(s), same networks and optimiser
+        torch.manual_seed(1)
+        other = FS.StepTrainer(B, H, W, dev, loss=name, ddp=world > 1, local_rank=local)
+        legs[name] = timed(other, max(5, args.steps // 2), 3)[0]
+        del other
+        torch.cuda.empty_cache()
+    if rank == 0:
+        line = {"metric": "training examples/s (full step: networks + fused view-synthesis loss + Adam)",
+                "value": B * world / (ms * 1e-3), "unit": "examples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "batch_per_gpu": B, "height": H, "width": W, "scales": 4,
+                           "frames": [0, -1, 1], "network_parameters": fused.n_params,
+                           "networks": "ResNet-18 encoder + skip decoder + 6-channel ResNet-18 pose encoder + pose head, "
+                                       "random init, plain torch/cuDNN fp32 (not the product)",
+                           "sharding": f"batch x{world}; DistributedDataParallel all-reduce of the network gradients over NCCL"
+                                       if world > 1 else "single GPU",
+                           "l2": "working set (activations of a 12-sample ResNet step) far exceeds the 126 MB L2",
+                           "timing": "CUDA events around K steps, max over ranks",
+                           "ms_per_step_networks_only": legs["none"],
+                           "ms_per_step_with_stock_pytorch_loss": legs["eager"],
+                           "loss_share_ms_fused": ms - legs["none"], "loss_share_ms_stock": legs["eager"] - legs["none"],
+                           "final_loss": loss},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": B * world / (e2e_wall * 1e-3), "unit": "examples/s", "ms_per_step": e2e_wall,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "how": "batch uploaded from pinned host memory every step, loss read back every step; wall clock"}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
 
 def main():
     args = parse()
-    if args.impl == "reference":
+    if args.workload in FULL_STEP:
+        if args.impl == "reference":
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the full-step workload has no CPU reference leg; "
+                                  "its stock-PyTorch leg is config.ms_per_step_with_stock_pytorch_loss"}))
+        else:
+            run_full_step(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
