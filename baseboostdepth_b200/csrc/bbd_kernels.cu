@@ -113,16 +113,20 @@ __global__ void __launch_bounds__(SCfg::NT, BBD_MIN_BLOCKS) reproj_kernel(const 
   const StripCtx t = make_strip<SCfg>(blockIdx.x, blockIdx.y, blockIdx.z, tid, a.batch, a.height, a.width);
   const int n_rep = a.tab.hdr[(size_t)t.b * 4];
 
-  rs_load_target<SCfg>(a, sm, t, tid);
+  rs_load_target<SCfg>(a, sm, t, tid);  // asynchronous copies, in flight during the first warp phase
   rs_begin_scale<SCfg>(sm, tid);
-  __syncthreads();
-  rs_target_stats<SCfg>(a, sm, t);
   {
     for (int k = 0; k < n_rep; ++k) {
       if (!KEEP && k) __syncthreads();  // the single warped-tile buffer is reused by every candidate
       rs_warp<SCfg, KEEP>(a, sm, t, k);
+      if (k == 0) rs_load_wait();
       __syncthreads();
+      if (k == 0) rs_target_stats<SCfg>(a, sm, t);  // each thread reads back only slots it wrote itself
       rs_stats<SCfg, KEEP>(a, sm, t, k);
+    }
+    if (n_rep == 0) {  // no warped candidate at all: the identity minimum wins everywhere
+      rs_load_wait();
+      __syncthreads();
     }
     const float part = rs_select<SCfg>(a, sm, t, n_rep);
     block_reduce<1>(sm.red, tid, &part, a.loss_part + ((size_t)t.s * a.batch + t.b) * t.ntiles + t.tile);

@@ -130,6 +130,26 @@ BBD_HD void w9pp_2(const float* x0, const float* x1, const float* y0, const floa
   }
 }
 
+// One word global -> shared.  On the device this is an asynchronous copy (LDGSTS: no register
+// staging, the thread does not wait for the data); rs_load_wait() must precede the barrier that
+// publishes it.
+BBD_HD void copy_word_async(float* dst, const float* src) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#else
+  *dst = *src;
+#endif
+}
+BBD_HD void rs_load_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
+// Target tile (3 channels) over R2, reflection resolved.  Asynchronous on the device: the kernel
+// overlaps it with the first candidate's warp phase (which does not read the target) and calls
+// rs_load_wait() before the barrier that precedes the first use of sm.tgt.  (Staging the depth
+// tile the same way was measured: no gain, its loads are already hidden.)
 template <class C>
 BBD_HD void rs_load_target(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t, int tid) {
   const int H = a.height, W = a.width, HW = H * W;
@@ -137,9 +157,9 @@ BBD_HD void rs_load_target(const bbd_reproj_args& a, StripSmem<C>& sm, const Str
   for (int j = t.warp; j < C::R2H; j += C::NW) {
     const int o = reflect1(t.y0 - 2 + j, H) * W + t.px;
     const int i = j * C::P + t.lane;
-    sm.tgt[i] = img[o];
-    sm.tgt[C::R2N + i] = img[HW + o];
-    sm.tgt[2 * C::R2N + i] = img[2 * HW + o];
+    copy_word_async(sm.tgt + i, img + o);
+    copy_word_async(sm.tgt + C::R2N + i, img + HW + o);
+    copy_word_async(sm.tgt + 2 * C::R2N + i, img + 2 * HW + o);
   }
 }
 

@@ -29,6 +29,7 @@ import torch  # noqa: E402
 METRIC = "warped px-pairs/s fwd+bwd (photometric loss)"
 UNIT = "px-pairs/s"
 DEFAULT_WORKLOAD = "kitti_640x192_b12_pm1"   # BASELINE.json configs[1]
+_REAL_STDOUT = 1
 
 
 def parse():
@@ -206,7 +207,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -451,7 +452,7 @@ def run_ours(args):
                 line["cpu_baseline"]["same_code_eager_cuda_ms_per_step"] = eager_cuda_ms(cfg, dev)
             except Exception as exc:  # noqa: BLE001
                 line["cpu_baseline"]["same_code_eager_cuda_ms_per_step"] = f"failed: {type(exc).__name__}"
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -552,18 +553,29 @@ def run_full_step(args):
                 "e2e": {"value": B * world / (e2e_wall * 1e-3), "unit": "examples/s", "ms_per_step": e2e_wall,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "how": "batch uploaded from pinned host memory every step, loss read back every step; wall clock"}}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line):
+    """The one JSON line, on the process's real stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    # Libraries may print on stdout (NCCL's version banner does when NCCL_DEBUG is set on the box);
+    # the contract is ONE JSON line there, so everything else is routed to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     if args.workload in FULL_STEP:
         if args.impl == "reference":
             if int(os.environ.get("RANK", "0")) == 0:
-                print(json.dumps({"impl": "reference", "unavailable": "the full-step workload has no CPU reference leg; "
-                                  "its stock-PyTorch leg is config.ms_per_step_with_stock_pytorch_loss"}))
+                emit({"impl": "reference", "unavailable": "the full-step workload has no CPU reference leg; "
+                      "its stock-PyTorch leg is config.ms_per_step_with_stock_pytorch_loss"})
         else:
             run_full_step(args)
     elif args.impl == "reference":
