@@ -436,6 +436,27 @@ __global__ void ssim_grad_kernel(int planes, int H, int W, const float* x, const
   }
 }
 
+// 16 bytes in, 64 bytes out per thread and iteration; n16 = number of 16-byte groups
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint4* __restrict__ src, float4* __restrict__ dst, size_t n16) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = src[i];
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float4 o;
+      o.x = u8_to_unit((uint8_t)(w[k] & 0xff));
+      o.y = u8_to_unit((uint8_t)((w[k] >> 8) & 0xff));
+      o.z = u8_to_unit((uint8_t)((w[k] >> 16) & 0xff));
+      o.w = u8_to_unit((uint8_t)(w[k] >> 24));
+      dst[i * 4 + k] = o;
+    }
+  }
+}
+__global__ void u8_to_f32_tail_kernel(const uint8_t* src, float* dst, size_t begin, size_t n) {
+  const size_t i = begin + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = u8_to_unit(src[i]);
+}
+
 static int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
   const size_t cap = 148 * 16;  // a few resident blocks per SM, grid-stride beyond that
@@ -660,6 +681,20 @@ int bbd_grid_sample_backward(int32_t n, int32_t channels, int32_t height, int32_
   grid_sample_grad_kernel<<<grid_for((size_t)n * out_h * out_w, 256), 256, 0, (cudaStream_t)stream>>>(
       n, channels, height, width, out_h * out_w, images, grid, gout, ggrid);
   return check_launch("grid_sample_grad_kernel");
+}
+
+int bbd_u8_to_f32(const uint8_t* src, float* dst, size_t n, bbd_stream_t stream) {
+  if (!src || !dst) return fail(BBD_E_ARG, "u8_to_f32: null argument");
+  if (n == 0) return 0;
+  const bool aligned = ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0);
+  const size_t n16 = aligned ? n / 16 : 0;
+  if (n16)
+    u8_to_f32_kernel<<<grid_for(n16, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(src),
+                                                                            reinterpret_cast<float4*>(dst), n16);
+  const size_t done = n16 * 16;
+  if (done < n)
+    u8_to_f32_tail_kernel<<<(unsigned)((n - done + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, done, n);
+  return check_launch("u8_to_f32_kernel");
 }
 
 int bbd_ssim_forward(int32_t n, int32_t channels, int32_t height, int32_t width, const float* x, const float* y, float* out,

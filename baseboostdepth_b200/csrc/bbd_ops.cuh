@@ -446,4 +446,7 @@ BBD_HD void ssim_grad_px(const float* x, const float* y, const float* gout, int 
   if (gy) gy[o] = ay + by * y[o] + cy * x[o];
 }
 
+// torchvision ToTensor on an 8-bit frame: float32(v) / 255, correctly rounded.
+BBD_HD float u8_to_unit(uint8_t v) { return div_((float)v, 255.0f); }
+
 }  // namespace bbd

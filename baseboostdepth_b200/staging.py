@@ -8,6 +8,7 @@ the previous batch is still being consumed; the compute stream only waits on an 
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from typing import Dict
 
@@ -35,36 +36,55 @@ def bind_to_gpu_numa(device_index: int) -> str:
 
 
 class BatchStager:
-    def __init__(self, template: Dict, device, slots: int = 2):
+    """``template``: key -> tensor.  float32 entries cross PCIe as they are.  uint8 entries are frames
+    as decoded: they cross at one byte per colour sample and are expanded on the device to the fp32
+    tensor ``torchvision.transforms.ToTensor`` would have produced on the host (``x / 255``,
+    bit-identical; reference ``datasets/mono_dataset.py:55,201-203``) by one ``bbd_u8_to_f32`` launch
+    on the copy stream, so the expansion also overlaps the previous step."""
+
+    def __init__(self, template: Dict, device, slots: int = 2, backend=None):
         self.device = torch.device(device)
-        self.keys, self.meta, off = [], {}, 0
+        self.keys, self.meta = [], {}
+        f_off = u_off = 0
         for k, v in template.items():
             if not torch.is_tensor(v):
                 continue
-            assert v.dtype == torch.float32, "the loss path is fp32"
+            assert v.dtype in (torch.float32, torch.uint8), "fp32 tensors or 8-bit frames"
             n = v.numel()
             self.keys.append(k)
-            self.meta[k] = (off, n, tuple(v.shape))
-            off += (n + 63) // 64 * 64                      # 256-byte aligned sub-buffers
-        self.total = off
-        self.host_arena = torch.empty(self.total, dtype=torch.float32).pin_memory()
-        self.host = {k: self._view(self.host_arena, k) for k in self.keys}
-        self.dev_arena = [torch.empty(self.total, dtype=torch.float32, device=self.device) for _ in range(slots)]
+            if v.dtype == torch.uint8:
+                self.meta[k] = ("u8", u_off, n, tuple(v.shape))
+                u_off += (n + 255) // 256 * 256             # 256-byte aligned sub-buffers
+            else:
+                self.meta[k] = ("f32", f_off, n, tuple(v.shape))
+                f_off += (n * 4 + 255) // 256 * 256
+        self.f32_bytes, self.u8_bytes = f_off, u_off
+        self.total = f_off + u_off                          # bytes: [ fp32 entries | 8-bit entries ]
+        self.host_arena = torch.empty(self.total, dtype=torch.uint8).pin_memory()
+        self.dev_arena = [torch.empty(self.total, dtype=torch.uint8, device=self.device) for _ in range(slots)]
+        # fp32 expansion of the 8-bit part of each slot
+        self.expanded = [torch.empty(max(u_off, 1), dtype=torch.float32, device=self.device) for _ in range(slots)]
+        self.host = {k: self._view(self.host_arena, None, k) for k in self.keys}
         self.ready = [torch.cuda.Event() for _ in range(slots)]
         self.consumed = [torch.cuda.Event() for _ in range(slots)]
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.slot = -1
+        self._backend = backend
         for k, v in template.items():
             if torch.is_tensor(v):
                 self.host[k].copy_(v.detach().cpu())
 
-    def _view(self, arena, k):
-        off, n, shape = self.meta[k]
-        return arena[off:off + n].view(shape)
+    def _view(self, arena, expanded, k):
+        kind, off, n, shape = self.meta[k]
+        if kind == "f32":
+            return arena[off:off + 4 * n].view(torch.float32).view(shape)
+        if expanded is None:                                # host side: the bytes themselves
+            return arena[self.f32_bytes + off:self.f32_bytes + off + n].view(shape)
+        return expanded[off:off + n].view(shape)
 
     @property
     def nbytes(self):
-        return self.total * 4
+        return self.total
 
     def upload_async(self):
         """Start copying the host arena into the next device slot (side stream); returns the slot."""
@@ -73,13 +93,18 @@ class BatchStager:
         self.copy_stream.wait_event(self.consumed[s])       # the previous user of this slot is done
         with torch.cuda.stream(self.copy_stream):
             self.dev_arena[s].copy_(self.host_arena, non_blocking=True)
+            if self.u8_bytes:
+                from . import _lib
+                be = self._backend if self._backend is not None else _lib.cuda_backend()
+                be.call("u8_to_f32", ctypes.c_void_p(self.dev_arena[s].data_ptr() + self.f32_bytes),
+                        ctypes.c_void_p(self.expanded[s].data_ptr()), ctypes.c_size_t(self.u8_bytes))
             self.ready[s].record(self.copy_stream)
         return s
 
     def views(self, slot):
-        """Device tensors of a slot; the current stream waits until its upload has landed."""
+        """Device tensors (all fp32) of a slot; the current stream waits until its upload has landed."""
         torch.cuda.current_stream().wait_event(self.ready[slot])
-        return {k: self._view(self.dev_arena[slot], k) for k in self.keys}
+        return {k: self._view(self.dev_arena[slot], self.expanded[slot], k) for k in self.keys}
 
     def release(self, slot):
         """Call after the last kernel reading the slot was enqueued."""

@@ -217,6 +217,12 @@ int bbd_ssim_forward(int32_t n, int32_t channels, int32_t height, int32_t width,
 int bbd_ssim_backward(int32_t n, int32_t channels, int32_t height, int32_t width, const float* x,
                       const float* y, const float* gout, float* gx, float* gy, bbd_stream_t stream);
 
+/* Frames as decoded (8-bit) -> the fp32 tensors the reference's loader hands the trainer:
+ * torchvision ToTensor = uint8 -> float32, IEEE division by 255 (datasets/mono_dataset.py:55,201-203).
+ * dst[i] = (float)src[i] / 255 for i < n, bit-identical to ToTensor.  Lets a batch cross PCIe at
+ * one byte per colour sample instead of four (staging.BatchStager). */
+int bbd_u8_to_f32(const uint8_t* src, float* dst, size_t n, bbd_stream_t stream);
+
 int bbd_version(void);
 const char* bbd_last_error_string(void);
 

@@ -339,4 +339,9 @@ int emu_ssim_backward(int32_t n, int32_t ch, int32_t H, int32_t W, const float* 
   return 0;
 }
 
+int emu_u8_to_f32(const uint8_t* src, float* dst, size_t n) {
+  for (size_t i = 0; i < n; ++i) dst[i] = u8_to_unit(src[i]);
+  return 0;
+}
+
 }  // extern "C"

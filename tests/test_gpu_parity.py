@@ -224,6 +224,27 @@ def test_batch_stager_roundtrip(cuda_device):
     torch.cuda.synchronize()
 
 
+def test_batch_stager_8bit_frames(cuda_device):
+    """8-bit frames cross PCIe as bytes and come out as the fp32 tensors ToTensor would have made
+    (datasets/mono_dataset.py:55,201-203: uint8 -> float32 / 255), next to fp32 entries; odd sizes."""
+    from baseboostdepth_b200.staging import BatchStager
+    gen = torch.Generator().manual_seed(2)
+    frame = torch.randint(0, 256, (2, 3, 37, 53), generator=gen, dtype=torch.uint8)
+    ramp = torch.arange(256, dtype=torch.uint8)
+    template = {("color", 0, 0): frame, "ramp": ramp, ("disp", 0): torch.rand(2, 1, 37, 53, generator=gen)}
+    st = BatchStager(template, cuda_device)
+    assert st.nbytes < frame.numel() * 2 + 256 * 2 + template[("disp", 0)].numel() * 4 + 1024
+    for it in range(3):
+        slot = st.upload_async()
+        v = st.views(slot)
+        assert v[("color", 0, 0)].dtype == torch.float32
+        assert torch.equal(v[("color", 0, 0)].cpu(), frame.to(torch.float32).div(255))
+        assert torch.equal(v["ramp"].cpu(), ramp.to(torch.float32).div(255))
+        assert torch.equal(v[("disp", 0)].cpu(), template[("disp", 0)])
+        st.release(slot)
+    torch.cuda.synchronize()
+
+
 def test_grid_sample_on_gpu(cuda_device):
     import torch.nn.functional as F
     import baseboostdepth_b200.layers as L
@@ -288,6 +309,62 @@ def test_step_is_cuda_graph_capturable(cuda_device):
     assert got_loss == want_loss
     for k, p in leaves.items():
         assert torch.equal(got[k], p.grad), k
+
+
+def test_graphed_step_over_staging_slots(cuda_device):
+    """graphed.GraphedLossStep: the step replayed as a CUDA graph per staging slot, batches changing on
+    the host between uploads, 8-bit frames; losses and gradients equal the eager evaluation."""
+    from baseboostdepth_b200.graphed import GraphedLossStep
+    from baseboostdepth_b200.staging import BatchStager
+    from baseboostdepth_b200.trainer import loss_step
+    cfg = dict(batch=2, height=64, width=96, baselines=[1, 1], trimin=False, decomp=False)
+    opt = O.default_opt(height=64, width=96, trimin=False, batch_size=2)
+    gi, go, gp = make_batch(seed=9, device="cpu", **cfg)
+    plan = plan_for(gi["ordering"], False, False, None)
+    template = {}
+    for k, v in gi.items():
+        if torch.is_tensor(v):
+            frame = isinstance(k, tuple) and k[0] == "color"
+            template[("in",) + (k if isinstance(k, tuple) else (k,))] = (v * 255).round().to(torch.uint8) if frame else v
+    for k, v in go.items():
+        if k[0] in ("disp", "cam_T_cam") and v.numel():
+            template[("leaf",) + k] = v.detach()
+    st = BatchStager(template, cuda_device)
+
+    def make_io(v):
+        gin, gout, lv = {"ordering": gi["ordering"]}, {}, {}
+        for k, t in v.items():
+            if k[0] == "in":
+                gin[k[1] if len(k) == 2 else k[1:]] = t
+            else:
+                gout[k[1:]] = lv[k[1:]] = t.detach().requires_grad_(True)
+        return gin, gout, lv
+
+    step = GraphedLossStep(st, make_io, opt, plan, num_scales=4)
+    got = []
+    slot = st.upload_async()
+    for it in range(4):
+        st.host[("leaf", "disp", 0)].mul_(0.9).add_(0.01)           # the next batch differs
+        nxt = st.upload_async()
+        torch.manual_seed(100 + it)                                  # noise drawn inside the graph
+        step.launch(slot)
+        grads = {k: g.clone() for k, g in step.grads(slot).items()}
+        # eager evaluation of the same slot contents with the same noise stream
+        gin, gout, lv = make_io(st.views(slot))
+        torch.manual_seed(100 + it)
+        want = loss_step(gin, gout, opt, plan, noise=None, num_scales=4)["loss"]
+        want.backward()
+        torch.cuda.synchronize()
+        v = step.collect()
+        if v is not None:
+            got.append(v)
+        for k, p in lv.items():
+            assert rel_l2(grads[k], p.grad) <= 1e-6, k
+        wants = float(want)
+        slot = nxt
+        last_want = wants
+    got.append(step.collect(final=True))
+    assert len(got) == 4 and abs(got[-1] - last_want) <= 2e-6
 
 
 def test_sql_mode_matches_oracle(cuda_device):

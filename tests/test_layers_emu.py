@@ -214,3 +214,13 @@ def test_grid_sample_matches_aten():
         res.append((out.detach(), raw.grad))
     assert max_abs(res[1][0], res[0][0]) <= 1e-6
     assert max_abs(res[1][1], res[0][1]) <= 1e-5
+
+
+def test_u8_to_f32_is_totensor():
+    """bbd_u8_to_f32 (kernel source stepped on the CPU) == torchvision ToTensor's arithmetic for all 256 codes."""
+    import ctypes
+    be = emu_backend()
+    src = torch.arange(256, dtype=torch.uint8).repeat(3)
+    dst = torch.empty(src.numel(), dtype=torch.float32)
+    be.call("u8_to_f32", ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()), ctypes.c_size_t(src.numel()))
+    assert torch.equal(dst, src.to(torch.float32).div(255))
