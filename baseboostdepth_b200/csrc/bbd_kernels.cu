@@ -14,10 +14,12 @@
 
 namespace bbd {
 
-// Identity pre-pass and fused loss share one tile geometry: 28x16 target pixels per block of 8
+// Identity pre-pass and fused loss share one tile geometry: 28x16 target pixels per block of 6
 // warps, lanes = columns (bbd_strip.cuh).  With two warped candidates a block needs 64 KB of shared
-// memory and 80 registers per thread -> 3 blocks (24 warps) per SM, the best of the measured
-// variants (profiles/README.md).
+// memory -> 3 blocks (18 warps) per SM at 96 registers per thread.  Fewer, fatter warps beat 8 warps
+// at 80 registers: the kernel gains from instruction-level parallelism inside a warp (four rows of
+// gathers in flight in the warp phase, two rows walked together in the backward), not from more
+// resident warps (profiles/README.md lists the measured variants).
 #ifndef BBD_TILE_H
 #define BBD_TILE_H 16
 #endif
@@ -25,7 +27,7 @@ namespace bbd {
 #define BBD_MIN_BLOCKS 3
 #endif
 #ifndef BBD_WARPS
-#define BBD_WARPS 8
+#define BBD_WARPS 6
 #endif
 using SCfg = StripCfg<BBD_TILE_H, BBD_WARPS>;
 
@@ -145,10 +147,14 @@ __global__ void __launch_bounds__(SCfg::NT, BBD_MIN_BLOCKS) reproj_kernel(const 
           rs_candidate(a, t.b, k, src, cam);
 #pragma unroll
           for (int i = 0; i < 12; ++i) gP[i] = 0.0f;
-          for (int q = t.warp; q < SCfg::TH; q += SCfg::NW) {  // warp-uniform
-            rs_bwd_vertical<SCfg>(a, sm, t, k, q);
+          for (int q = t.warp; q < SCfg::TH; q += BBD_BWD_ROWS * SCfg::NW) {  // warp-uniform
+#pragma unroll
+            for (int r = 0; r < BBD_BWD_ROWS; ++r)
+              if (q + r * SCfg::NW < SCfg::TH) rs_bwd_vertical<SCfg>(a, sm, t, k, q + r * SCfg::NW, r);
             __syncwarp();
-            rs_bwd_horizontal<SCfg, KEEP>(a, sm, t, k, q, src, cam, gP);
+#pragma unroll
+            for (int r = 0; r < BBD_BWD_ROWS; ++r)
+              if (q + r * SCfg::NW < SCfg::TH) rs_bwd_horizontal<SCfg, KEEP>(a, sm, t, k, q + r * SCfg::NW, src, cam, gP, r);
             __syncwarp();
           }
         }

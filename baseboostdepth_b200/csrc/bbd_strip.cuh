@@ -15,13 +15,16 @@
 #include "bbd_common.cuh"
 
 #ifndef BBD_UNROLL_WARP
-#define BBD_UNROLL_WARP 3
+#define BBD_UNROLL_WARP 4
 #endif
 #ifndef BBD_UNROLL_STATS
 #define BBD_UNROLL_STATS 1
 #endif
 #ifndef BBD_PACKED_STATS
 #define BBD_PACKED_STATS 1
+#endif
+#ifndef BBD_BWD_ROWS
+#define BBD_BWD_ROWS 2  // rows a warp walks together in the backward (one exchange buffer each)
 #endif
 #define BBD_PRAGMA(x) _Pragma(#x)
 #define BBD_UNROLL(n) BBD_PRAGMA(unroll n)
@@ -57,8 +60,8 @@ struct StripSmem {
     tgt = base; base += 3 * C::R2N;
     pred = base; base += (size_t)npred * 3 * C::R2N;
     tst = base; base += 6 * C::R1N;
+    best = base; base += C::R1N;     // directly behind tst: together they host the backward's exchange buffers
     stash = base; base += 9 * C::R1N;
-    best = base; base += C::R1N;
     bidx = reinterpret_cast<int*>(base); base += C::R1N;
     gd = base; base += C::INN;
     red = base; base += C::NW * 12;
@@ -394,14 +397,14 @@ BBD_HD float rs_select(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCt
 // statistics planes, which are dead once the winners are selected), so the two passes are
 // separated by a warp barrier only.
 template <class C>
-BBD_HD float* rs_xch(StripSmem<C>& sm, const StripCtx& t) { return sm.tst + t.warp * 320; }
+BBD_HD float* rs_xch(StripSmem<C>& sm, const StripCtx& t, int buf) { return sm.tst + (t.warp * BBD_BWD_ROWS + buf) * 320; }
 
 template <class C>
-BBD_HD void rs_bwd_vertical(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t, int k, int q) {
-  static_assert(C::NW * 320 <= 6 * C::R1N, "exchange buffers must fit the target statistics planes");
+BBD_HD void rs_bwd_vertical(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t, int k, int q, int buf = 0) {
+  static_assert(C::NW * BBD_BWD_ROWS * 320 <= 7 * C::R1N, "exchange buffers must fit the planes that are dead after the selection");
   const int py = t.y0 + q;
   if (py >= a.height || t.lane < 1 || t.lane > 30) return;
-  float* x = rs_xch<C>(sm, t);
+  float* x = rs_xch<C>(sm, t, buf);
   const float my0 = (py == 1) ? 2.0f : 1.0f, my2 = (py == a.height - 2) ? 2.0f : 1.0f;
   float v[9];
 #pragma unroll
@@ -423,11 +426,11 @@ BBD_HD void rs_bwd_vertical(const bbd_reproj_args& a, StripSmem<C>& sm, const St
 
 template <class C, bool KEEP>
 BBD_HD void rs_bwd_horizontal(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t, int k, int q,
-                              const float* src, const Cam& cam, float gP[12]) {
+                              const float* src, const Cam& cam, float gP[12], int buf = 0) {
   const int H = a.height, W = a.width, HW = H * W;
   const int py = t.y0 + q;
   if (py >= H || t.lane < 2 || t.lane > 29 || t.u >= W) return;
-  const float* x = rs_xch<C>(sm, t);
+  const float* x = rs_xch<C>(sm, t, buf);
   if (x[9 * 32 + t.lane - 1] + x[9 * 32 + t.lane] + x[9 * 32 + t.lane + 1] == 0.0f) return;
   const float wgt = 1.0f / ((float)a.batch * (float)H * (float)W);
   const float g_l1 = a.no_ssim ? wgt * BBD_THIRD : wgt * BBD_W_L1 * BBD_THIRD;

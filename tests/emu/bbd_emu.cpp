@@ -20,7 +20,7 @@ using namespace bbd;
 #ifndef BBD_TILE_H
 #define BBD_TILE_H 16
 #endif
-using SCfg = StripCfg<BBD_TILE_H, 8>;
+using SCfg = StripCfg<BBD_TILE_H, 6>;
 #define FOR_STID for (int tid = 0; tid < SCfg::NT; ++tid)
 
 extern "C" {
@@ -121,9 +121,11 @@ int emu_reproj_fused(const bbd_reproj_args* ap) {
               Cam cam;
               rs_candidate(a, b, k, src, cam);
               for (size_t i = 0; i < gPs.size(); ++i) gPs[i] = 0.0f;
-              for (int m = 0; m * SCfg::NW < SCfg::TH; ++m) {   // one row per warp at a time, lanes in lockstep
-                FOR_STID { const int q = ctx[tid].warp + m * SCfg::NW; if (q < SCfg::TH) rs_bwd_vertical<SCfg>(a, sm, ctx[tid], k, q); }
-                FOR_STID { const int q = ctx[tid].warp + m * SCfg::NW; if (q < SCfg::TH) { if (keep) rs_bwd_horizontal<SCfg, true>(a, sm, ctx[tid], k, q, src, cam, &gPs[(size_t)tid * 12]); else rs_bwd_horizontal<SCfg, false>(a, sm, ctx[tid], k, q, src, cam, &gPs[(size_t)tid * 12]); } }
+              for (int m = 0; m * SCfg::NW < SCfg::TH; m += BBD_BWD_ROWS) {   // BBD_BWD_ROWS rows per warp at a time, lanes in lockstep
+                for (int r = 0; r < BBD_BWD_ROWS; ++r)
+                  FOR_STID { const int q = ctx[tid].warp + (m + r) * SCfg::NW; if (q < SCfg::TH) rs_bwd_vertical<SCfg>(a, sm, ctx[tid], k, q, r); }
+                for (int r = 0; r < BBD_BWD_ROWS; ++r)
+                  FOR_STID { const int q = ctx[tid].warp + (m + r) * SCfg::NW; if (q < SCfg::TH) { if (keep) rs_bwd_horizontal<SCfg, true>(a, sm, ctx[tid], k, q, src, cam, &gPs[(size_t)tid * 12], r); else rs_bwd_horizontal<SCfg, false>(a, sm, ctx[tid], k, q, src, cam, &gPs[(size_t)tid * 12], r); } }
               }
             }
             FOR_STID rs_park<SCfg, 12>(sm.red, tid, &gPs[(size_t)tid * 12]);
