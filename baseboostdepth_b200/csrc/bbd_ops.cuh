@@ -67,44 +67,50 @@ BBD_HD size_t d2d_scratch_offset(const bbd_d2d_args& a, int lvl) {
     if (d2d_sep_factor(a, l)) off += (size_t)a.batch * a.height * a.w[l];
   return off;
 }
-// pass 1: for one full-resolution row oy and one low-resolution column ix, the weighted sum over
-// the 2F+2 outputs that can have ix as a tap (chain rule of disp_to_depth applied on the fly)
+// Weight of full-resolution output o = F*i + t for low-resolution input i, t in [-F/2, 3F/2): the
+// transpose of d2d_up for an integer factor F.  src(o) - i = (t + 0.5)/F - 0.5 is a dyadic number,
+// so up_taps computes l0/l1 exactly and the tent below reproduces them bit for bit.  At the clamped
+// borders both taps of the outer half-cell fall on the border input: its weight there is 1.
 template <int F>
-BBD_HD float d2d_hpass(const bbd_d2d_args& a, int lvl, int b, int oy, int ix, float sx) {
-  constexpr int N = 2 * F + 2;
+BBD_HD float d2d_tent(int t, int i, int in_size) {
+  float wgt = 1.0f - fabsf(((float)t + 0.5f) * (1.0f / (float)F) - 0.5f);
+  if (i == 0 && t < F / 2) wgt = 1.0f;
+  if (i == in_size - 1 && t >= F / 2) wgt = 1.0f;
+  return wgt;
+}
+// pass 1: for one full-resolution row oy and one low-resolution column ix, the weighted sum over
+// the 2F outputs that have ix as a tap (chain rule of disp_to_depth applied on the fly)
+template <int F>
+BBD_HD float d2d_hpass(const bbd_d2d_args& a, int lvl, int b, int oy, int ix) {
   const int w = a.w[lvl], H = a.height, W = a.width;
   const size_t plane = ((size_t)lvl * a.batch + b) * H * W + (size_t)oy * W;
   const float* gd = a.gdepth + plane;
   const float* dep = a.depth + plane;
   const float nspan = -a.disp_span;
-  const int ox0 = ix * F - F / 2 - 1;
+  const int ox0 = ix * F - F / 2;
   float acc = 0.0f;
 #pragma unroll
-  for (int k = 0; k < N; ++k) {
+  for (int k = 0; k < 2 * F; ++k) {
     const int ox = ox0 + k;
     if (ox < 0 || ox >= W) continue;
-    const float wx = d2d_axis_weight(ox, ix, w, sx);
-    if (wx == 0.0f) continue;
     float v = gd[ox];
     if (!a.sql) { const float d = dep[ox]; v *= nspan * d * d; }
-    acc += wx * v;
+    acc += d2d_tent<F>(k - F / 2, ix, w) * v;
   }
   return acc;
 }
-// pass 2: weighted sum of the row sums over the 2F+2 rows that can have iy as a tap
+// pass 2: weighted sum of the row sums over the 2F rows that have iy as a tap
 template <int F>
-BBD_HD float d2d_vpass(const bbd_d2d_args& a, int lvl, int b, int iy, int ix, float sy) {
-  constexpr int N = 2 * F + 2;
+BBD_HD float d2d_vpass(const bbd_d2d_args& a, int lvl, int b, int iy, int ix) {
   const int h = a.h[lvl], w = a.w[lvl], H = a.height;
   const float* tmp = a.scratch + d2d_scratch_offset(a, lvl) + (size_t)b * H * w;
-  const int oy0 = iy * F - F / 2 - 1;
+  const int oy0 = iy * F - F / 2;
   float acc = 0.0f;
 #pragma unroll
-  for (int k = 0; k < N; ++k) {
+  for (int k = 0; k < 2 * F; ++k) {
     const int oy = oy0 + k;
     if (oy < 0 || oy >= H) continue;
-    const float wy = d2d_axis_weight(oy, iy, h, sy);
-    if (wy != 0.0f) acc += wy * tmp[(size_t)oy * w + ix];
+    acc += d2d_tent<F>(k - F / 2, iy, h) * tmp[(size_t)oy * w + ix];
   }
   return acc;
 }
@@ -154,11 +160,11 @@ BBD_HD float d2d_backward_px(const bbd_d2d_args& a, int lvl, int b, int iy, int 
     acc = gd[o];
     if (!a.sql) acc *= nspan * dep[o] * dep[o];
   } else if (a.scratch && H == 2 * h && W == 2 * w) {
-    acc = d2d_vpass<2>(a, lvl, b, iy, ix, sy);
+    acc = d2d_vpass<2>(a, lvl, b, iy, ix);
   } else if (a.scratch && H == 4 * h && W == 4 * w) {
-    acc = d2d_vpass<4>(a, lvl, b, iy, ix, sy);
+    acc = d2d_vpass<4>(a, lvl, b, iy, ix);
   } else if (a.scratch && H == 8 * h && W == 8 * w) {
-    acc = d2d_vpass<8>(a, lvl, b, iy, ix, sy);
+    acc = d2d_vpass<8>(a, lvl, b, iy, ix);
   } else {
     // src(o) = (o + 0.5)/f - 0.5 lies in (i-1, i+1) for o in [f*i - f/2, f*i + 3f/2 - 1]; one extra
     // output on each side covers the clamped borders and rounding

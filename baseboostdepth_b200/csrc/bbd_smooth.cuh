@@ -107,17 +107,22 @@ BBD_HD void sm_stage2_thread(const SmoothArgs& a, int lvl, int b, int chunk, int
   out[2] = sgd;
 }
 
-BBD_HD void sm_stage3_thread(const SmoothArgs& a, int lvl, int b, int chunk, int tid, float mean) {
+// sum over the sample of g_d * disp (stage 2 partials), once per block
+BBD_HD float sm_sample_gd_dot(const SmoothArgs& a, int lvl, int b) {
+  const float* p = sm_slot(a, lvl, b, 3);
+  const int nc = sm_chunks(a.h[lvl], a.w[lvl]);
+  float s = 0.0f;
+  for (int i = 0; i < nc; ++i) s += p[i];
+  return s;
+}
+
+BBD_HD void sm_stage3_thread(const SmoothArgs& a, int lvl, int b, int chunk, int tid, float mean, float gd_dot) {
   if (!a.gdisp[lvl]) return;
   const int n = a.h[lvl] * a.w[lvl];
   float* g = a.gdisp[lvl] + (size_t)b * n;
   if (!a.normalize) return;  // g_d already is the gradient
   const float den = add(mean, 1e-7f);
-  const float* p = sm_slot(a, lvl, b, 3);
-  const int nc = sm_chunks(a.h[lvl], a.w[lvl]);
-  float s = 0.0f;
-  for (int i = 0; i < nc; ++i) s += p[i];
-  const float coupling = s / ((float)n * den * den);
+  const float coupling = gd_dot / ((float)n * den * den);
   const float inv = 1.0f / den;
   for (int i = chunk * SM_CHUNK + tid; i < (chunk + 1) * SM_CHUNK && i < n; i += SM_NT) g[i] = g[i] * inv - coupling;
 }

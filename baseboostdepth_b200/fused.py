@@ -24,6 +24,18 @@ from . import _lib
 from .plan import LossPlan
 
 
+_SIDE: Dict = {}
+
+
+def _side_stream(device):
+    """One helper stream per device: the disparity -> depth and smoothness kernels (small, latency-bound)
+    run on it next to the identity pre-pass and join the launch stream before the fused kernel."""
+    s = _SIDE.get(device)
+    if s is None:
+        s = _SIDE[device] = torch.cuda.Stream(device=device)
+    return s
+
+
 def _tables(plan: LossPlan, device):
     cache = getattr(plan, "_dev_tables", None)
     if cache is None or cache[0] != str(device):
@@ -87,7 +99,45 @@ class _FusedLoss(torch.autograd.Function):
             d2d.h[l], d2d.w[l] = d.shape[2], d.shape[3]
             d2d.disp[l] = d.data_ptr()
         d2d.depth = depth.data_ptr()
-        be.call("disp_to_depth_forward", C.byref(d2d))
+
+        # 5 (prepared here, see below). smoothness on the disparity pyramid
+        sa = _lib.SmoothArgs()
+        sa.batch, sa.levels, sa.normalize = B, S, 1
+        gsm = []
+        smooth_src = disps_c
+        for l, d in enumerate(smooth_src):
+            img = pyramid[l].contiguous()
+            keep.append(img)
+            assert img.shape[0] == B and img.shape[-2:] == d.shape[-2:], (img.shape, d.shape)
+            sa.h[l], sa.w[l] = d.shape[2], d.shape[3]
+            sa.disp[l], sa.img[l] = d.data_ptr(), img.data_ptr()
+            if need_grad:
+                g = torch.empty_like(d)
+                gsm.append(g)
+                sa.gdisp[l] = g.data_ptr()
+        hs = (C.c_int32 * S)(*[d.shape[2] for d in smooth_src])
+        ws = (C.c_int32 * S)(*[d.shape[3] for d in smooth_src])
+        scratch = torch.empty(max(1, be.value("smooth_scratch_floats", B, S, hs, ws)), **f32)
+        smooth = torch.empty(S, **f32)
+        sa.scratch, sa.loss = scratch.data_ptr(), smooth.data_ptr()
+
+        # Steps 1 and 5 depend only on the disparities and the colour pyramid.  Every buffer they write
+        # was allocated above on the launch stream, so they can run on the helper stream between a
+        # fork and a join event while the identity pre-pass (step 2) runs here.
+        join = None
+        if be.cuda:
+            main, side = torch.cuda.current_stream(), _side_stream(dev)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                be.call("disp_to_depth_forward", C.byref(d2d))
+                be.call("smooth_fused", C.byref(sa))
+                join = torch.cuda.Event()
+                join.record(side)
+        else:
+            be.call("disp_to_depth_forward", C.byref(d2d))
+            be.call("smooth_fused", C.byref(sa))
 
         # 2. identity pre-pass (once per step)
         ident_min = torch.empty(B, H, W, **f32)
@@ -107,6 +157,8 @@ class _FusedLoss(torch.autograd.Function):
         ia.ident_min = ident_min.data_ptr()
         ia.ident_arg = _lib.ptr(ident_arg)
         be.call("ident_forward", C.byref(ia))
+        if join is not None:
+            torch.cuda.current_stream().wait_event(join)
 
         # 3. fused warp + photometric + min (+ gradients)
         ntiles = be.value("reproj_tiles", H, W)
@@ -135,28 +187,6 @@ class _FusedLoss(torch.autograd.Function):
         reproj = torch.empty(S, **f32)
         gpose = torch.empty(S, plan.n_pose, 3, 4, **f32) if need_grad else None
         be.call("reproj_finalize", C.byref(ra), C.c_void_p(reproj.data_ptr()), C.c_void_p(_lib.ptr(gpose)))
-
-        # 5. smoothness on the disparity pyramid
-        sa = _lib.SmoothArgs()
-        sa.batch, sa.levels, sa.normalize = B, S, 1
-        gsm = []
-        smooth_src = disps_c
-        for l, d in enumerate(smooth_src):
-            img = pyramid[l].contiguous()
-            keep.append(img)
-            assert img.shape[0] == B and img.shape[-2:] == d.shape[-2:], (img.shape, d.shape)
-            sa.h[l], sa.w[l] = d.shape[2], d.shape[3]
-            sa.disp[l], sa.img[l] = d.data_ptr(), img.data_ptr()
-            if need_grad:
-                g = torch.empty_like(d)
-                gsm.append(g)
-                sa.gdisp[l] = g.data_ptr()
-        hs = (C.c_int32 * S)(*[d.shape[2] for d in smooth_src])
-        ws = (C.c_int32 * S)(*[d.shape[3] for d in smooth_src])
-        scratch = torch.empty(max(1, be.value("smooth_scratch_floats", B, S, hs, ws)), **f32)
-        smooth = torch.empty(S, **f32)
-        sa.scratch, sa.loss = scratch.data_ptr(), smooth.data_ptr()
-        be.call("smooth_fused", C.byref(sa))
 
         ctx.cfg = cfg
         ctx.d2d = d2d

@@ -206,8 +206,9 @@ int emu_smooth_fused(const bbd_smooth_args* in) {
   for (int lvl = 0; lvl < a.levels; ++lvl) {
     for (int b = 0; b < a.batch; ++b) {
       const float mean = sm_sample_mean(a, lvl, b);
+      const float gd_dot = sm_sample_gd_dot(a, lvl, b);
       for (int c = 0; c < sm_chunks(a.h[lvl], a.w[lvl]); ++c)
-        for (int tid = 0; tid < SM_NT; ++tid) sm_stage3_thread(a, lvl, b, c, tid, mean);
+        for (int tid = 0; tid < SM_NT; ++tid) sm_stage3_thread(a, lvl, b, c, tid, mean, gd_dot);
     }
     float tot[2];
     for (int k = 0; k < 2; ++k) {
@@ -245,11 +246,10 @@ int emu_disp_to_depth_backward(const bbd_d2d_args* ap) {
       const int f = d2d_sep_factor(a, lvl);
       if (!f) continue;
       const int w = a.w[lvl], H = a.height;
-      const float sx = (float)w / (float)a.width;
       float* tmp = a.scratch + d2d_scratch_offset(a, lvl);
       for (int i = 0; i < a.batch * H * w; ++i) {
         const int ix = i % w, r = i / w, oy = r % H, b = r / H;
-        tmp[i] = f == 2 ? d2d_hpass<2>(a, lvl, b, oy, ix, sx) : (f == 4 ? d2d_hpass<4>(a, lvl, b, oy, ix, sx) : d2d_hpass<8>(a, lvl, b, oy, ix, sx));
+        tmp[i] = f == 2 ? d2d_hpass<2>(a, lvl, b, oy, ix) : (f == 4 ? d2d_hpass<4>(a, lvl, b, oy, ix) : d2d_hpass<8>(a, lvl, b, oy, ix));
       }
     }
   for (int lvl = 0; lvl < a.levels; ++lvl) {
