@@ -8,7 +8,7 @@ from fused_util import mirror_to_device, run_fused
 from baseboostdepth_b200.trainer import materialise_warps
 
 dev = torch.device("cuda:0")
-for case in ("plain_mixed_s", "trimin_decomp"):
+for case in ("plain_mixed_s", "trimin_decomp", "ragged_40x72", "small_16x24_b1"):
     h = Golden(case)
     hi, ho, leaves = mirror_to_device(h.inputs, h.outputs, h.params, dev)
     noise = {k: v.to(dev) for k, v in h.noise.items()}
