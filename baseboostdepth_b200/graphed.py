@@ -20,6 +20,9 @@ critical path.
 
 ``make_io(views) -> (inputs, outputs, leaves)`` maps the stager's device views of one slot to the
 trainer's ``inputs`` / ``outputs`` dictionaries and names the tensors that need gradients.
+``prepare(outputs)`` (optional) runs inside the captured step on a copy of ``outputs``: tensor ops that
+derive further entries from the uploaded ones, like the error-induced poses of ``--decomp``
+(``trainer.py:376-377``).
 """
 from __future__ import annotations
 
@@ -31,7 +34,8 @@ from .trainer import loss_step
 
 
 class GraphedLossStep:
-    def __init__(self, stager, make_io: Callable, opt, plan, num_scales: Optional[int] = None, warmup: int = 3):
+    def __init__(self, stager, make_io: Callable, opt, plan, num_scales: Optional[int] = None, warmup: int = 3,
+                 prepare: Optional[Callable] = None):
         self.stager = stager
         self._graphs, self._loss, self._leaves = [], [], []
         n_slots = len(stager.dev_arena)
@@ -48,7 +52,10 @@ class GraphedLossStep:
             def run():
                 for p in leaves.values():
                     p.grad = None
-                losses = loss_step(inputs, dict(outputs), opt, plan, noise=None, num_scales=num_scales)
+                outs = dict(outputs)
+                if prepare is not None:                      # e.g. the decomp error poses, derived from T in-graph
+                    prepare(outs)
+                losses = loss_step(inputs, outs, opt, plan, noise=None, num_scales=num_scales)
                 losses["loss"].backward()
                 return losses["loss"]
 
