@@ -166,44 +166,52 @@ __global__ void __launch_bounds__(SCfg::NT, BBD_MIN_BLOCKS) reproj_kernel(const 
 }
 
 // Sum the per-tile partials in a fixed order.  grid.x = S * (1 + num_pose); block 0..S-1 -> loss.
-__global__ void __launch_bounds__(128) reproj_finalize_kernel(const bbd_reproj_args a, float* loss, float* gpose, int ntiles) {
-  __shared__ float red[128];
+// 768 threads = 64 tile-lanes x 12 components: every thread adds its share of the partials, a
+// fixed-order tail adds the lanes (deterministic, no atomics).
+constexpr int FIN_NT = 768, FIN_LANES = FIN_NT / 12;
+__global__ void __launch_bounds__(FIN_NT) reproj_finalize_kernel(const bbd_reproj_args a, float* loss, float* gpose, int ntiles) {
+  __shared__ float red[FIN_NT];
+  __shared__ float red2[32];
   const int tid = threadIdx.x;
   const int S = a.num_scales;
   if ((int)blockIdx.x < S) {
     const int s = blockIdx.x;
     const float* p = a.loss_part + (size_t)s * a.batch * ntiles;
     float acc = 0.0f;
-    for (int i = tid; i < a.batch * ntiles; i += 128) acc += p[i];
+    for (int i = tid; i < a.batch * ntiles; i += FIN_NT) acc += p[i];
     red[tid] = acc;
+    __syncthreads();
+    if (tid < 32) {
+      float part = 0.0f;
+      for (int i = 0; i < FIN_NT / 32; ++i) part += red[tid * (FIN_NT / 32) + i];
+      red2[tid] = part;
+    }
     __syncthreads();
     if (tid == 0) {
       float tot = 0.0f;
-      for (int i = 0; i < 128; ++i) tot += red[i];
+      for (int i = 0; i < 32; ++i) tot += red2[i];
       loss[s] = tot / ((float)a.batch * (float)a.height * (float)a.width);
     }
     return;
   }
   if (!gpose) return;
-  // one block per (scale, pose row): find the (sample, candidate) that uses this pose, then
-  // 10 tile-lanes x 12 components sum the tile partials; a fixed-order tail adds the lanes.
+  // one block per (scale, pose row): find the (sample, candidate) pairs that use this pose
   const int idx = blockIdx.x - S, s = idx / a.num_pose, pose = idx % a.num_pose;
-  const int comp = tid % 12, lane = tid / 12;  // lanes 0..9 (tid < 120)
+  const int comp = tid % 12, lane = tid / 12;
   float acc = 0.0f;
   for (int b = 0; b < a.batch; ++b) {
     const int n_rep = a.tab.hdr[(size_t)b * 4];
     for (int k = 0; k < n_rep; ++k) {
       if (a.tab.rep[((size_t)b * BBD_MAX_REP + k) * 4 + 2] != pose) continue;
       const float* p = a.gpose_part + (((size_t)s * a.batch + b) * BBD_MAX_REP + k) * ntiles * 12;
-      if (tid < 120)
-        for (int tI = lane; tI < ntiles; tI += 10) acc += p[(size_t)tI * 12 + comp];
+      for (int tI = lane; tI < ntiles; tI += FIN_LANES) acc += p[(size_t)tI * 12 + comp];
     }
   }
   red[tid] = acc;
   __syncthreads();
   if (tid < 12) {
     float tot = 0.0f;
-    for (int l = 0; l < 10; ++l) tot += red[l * 12 + tid];
+    for (int l = 0; l < FIN_LANES; ++l) tot += red[l * 12 + tid];
     gpose[((size_t)s * a.num_pose + pose) * 12 + tid] = tot;
   }
 }
@@ -453,6 +461,15 @@ __global__ void ssim_grad_kernel(int planes, int H, int W, const float* x, const
   }
 }
 
+__global__ void loss_combine_kernel(int n, const float* reproj, const float* smooth, const float* weight, float num_scales,
+                                    float* per_scale, float* total) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) loss_combine(n, reproj, smooth, weight, num_scales, per_scale, total);
+}
+__global__ void loss_combine_grad_kernel(int n, const float* g_total, const float* g_per_scale, const float* weight,
+                                         float num_scales, float* g_reproj, float* g_smooth) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) loss_combine_grad(n, g_total, g_per_scale, weight, num_scales, g_reproj, g_smooth);
+}
+
 // 16 bytes in, 64 bytes out per thread and iteration; n16 = number of 16-byte groups
 __global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint4* __restrict__ src, float4* __restrict__ dst, size_t n16) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
@@ -535,7 +552,7 @@ int bbd_reproj_finalize(const bbd_reproj_args* a, float* loss, float* gpose, bbd
   if (gpose && !a->gpose_part) return fail(BBD_E_ARG, "finalize: no pose partials");
   const int ntiles = bbd_reproj_tiles(a->height, a->width);
   const int blocks = a->num_scales * (1 + (gpose ? a->num_pose : 0));
-  reproj_finalize_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(*a, loss, gpose, ntiles);
+  reproj_finalize_kernel<<<blocks, FIN_NT, 0, (cudaStream_t)stream>>>(*a, loss, gpose, ntiles);
   return check_launch("reproj_finalize_kernel");
 }
 
@@ -704,6 +721,22 @@ int bbd_grid_sample_backward(int32_t n, int32_t channels, int32_t height, int32_
   grid_sample_grad_kernel<<<grid_for((size_t)n * out_h * out_w, 256), 256, 0, (cudaStream_t)stream>>>(
       n, channels, height, width, out_h * out_w, images, grid, gout, ggrid);
   return check_launch("grid_sample_grad_kernel");
+}
+
+int bbd_loss_combine_forward(int32_t n, const float* reproj, const float* smooth, const float* weight, float num_scales,
+                             float* per_scale, float* total, bbd_stream_t stream) {
+  if (!reproj || !smooth || !weight || !per_scale || !total) return fail(BBD_E_ARG, "loss_combine: null argument");
+  if (n < 1 || n > BBD_MAX_SCALES || !(num_scales > 0.0f)) return fail(BBD_E_RANGE, "loss_combine: bad term count");
+  loss_combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(n, reproj, smooth, weight, num_scales, per_scale, total);
+  return check_launch("loss_combine_kernel");
+}
+
+int bbd_loss_combine_backward(int32_t n, const float* g_total, const float* g_per_scale, const float* weight,
+                              float num_scales, float* g_reproj, float* g_smooth, bbd_stream_t stream) {
+  if (!weight || !g_reproj || !g_smooth) return fail(BBD_E_ARG, "loss_combine backward: null argument");
+  if (n < 1 || n > BBD_MAX_SCALES || !(num_scales > 0.0f)) return fail(BBD_E_RANGE, "loss_combine: bad term count");
+  loss_combine_grad_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(n, g_total, g_per_scale, weight, num_scales, g_reproj, g_smooth);
+  return check_launch("loss_combine_grad_kernel");
 }
 
 int bbd_u8_to_f32(const uint8_t* src, float* dst, size_t n, bbd_stream_t stream) {

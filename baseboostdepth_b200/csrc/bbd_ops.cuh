@@ -452,6 +452,27 @@ BBD_HD void ssim_grad_px(const float* x, const float* y, const float* gout, int 
   if (gy) gy[o] = ay + by * y[o] + cy * x[o];
 }
 
+// ---- loss assembly (trainer.py:557-570), a handful of scalars: one thread ---------------------------
+BBD_HD void loss_combine(int n, const float* reproj, const float* smooth, const float* weight, float num_scales,
+                         float* per_scale, float* total) {
+  float tot = 0.0f;
+  for (int s = 0; s < n; ++s) {
+    const float l = add(reproj[s], mul(weight[s], smooth[s]));
+    per_scale[s] = l;
+    tot = (s == 0) ? l : add(tot, l);
+  }
+  *total = div_(tot, num_scales);
+}
+BBD_HD void loss_combine_grad(int n, const float* g_total, const float* g_per_scale, const float* weight,
+                              float num_scales, float* g_reproj, float* g_smooth) {
+  const float gt = g_total ? div_(*g_total, num_scales) : 0.0f;
+  for (int s = 0; s < n; ++s) {
+    const float g = gt + (g_per_scale ? g_per_scale[s] : 0.0f);
+    g_reproj[s] = g;
+    g_smooth[s] = g * weight[s];
+  }
+}
+
 // torchvision ToTensor on an 8-bit frame: float32(v) / 255, correctly rounded.
 BBD_HD float u8_to_unit(uint8_t v) { return div_((float)v, 255.0f); }
 

@@ -63,6 +63,77 @@ def _frame_ptrs(plan: LossPlan, frames: Dict, height, width):
     return arr, keep
 
 
+def disps_key(disps):
+    """Identity of a disparity list (a started side branch is valid for exactly this memory)."""
+    return tuple((d.data_ptr(), tuple(d.shape), d._version) for d in disps)
+
+
+def start_side_branch(be, disps, pyramid, bhw, min_depth, max_depth, sql, need_grad):
+    """Launch disparity -> depth (reference ``trainer.py:456`` + ``layers.py:13-22``) and the smoothness
+    kernels (``trainer.py:560-564``) for one step.  They depend only on the disparities and the colour
+    pyramid, are small and latency-bound, and therefore run on a helper stream between a fork and a
+    join event (graph-capturable) while the launch stream goes on with the pose packing, the noise
+    draw and the identity pre-pass; ``_FusedLoss.forward`` waits for ``join`` before the fused kernel.
+    Every buffer is allocated here on the launch stream, before the fork."""
+    B, H, W = bhw
+    S = len(disps)
+    assert 1 <= S <= _lib.MAX_SCALES
+    be.check_device(*disps, *pyramid)
+    dev = disps[0].device
+    f32 = dict(device=dev, dtype=torch.float32)
+    disps_c = [d.detach().contiguous() for d in disps]
+    keep = []
+    depth = torch.empty(S, B, H, W, **f32)
+    d2d = _lib.D2DArgs()
+    d2d.batch, d2d.levels, d2d.height, d2d.width = B, S, H, W
+    d2d.min_disp = 1 / max_depth
+    d2d.disp_span = 1 / min_depth - 1 / max_depth
+    d2d.sql = int(sql)
+    for l, d in enumerate(disps_c):
+        d2d.h[l], d2d.w[l] = d.shape[2], d.shape[3]
+        d2d.disp[l] = d.data_ptr()
+    d2d.depth = depth.data_ptr()
+
+    sa = _lib.SmoothArgs()
+    sa.batch, sa.levels, sa.normalize = B, S, 1
+    gsm = []
+    for l, d in enumerate(disps_c):
+        img = pyramid[l].contiguous()
+        keep.append(img)
+        assert img.shape[0] == B and img.shape[-2:] == d.shape[-2:], (img.shape, d.shape)
+        sa.h[l], sa.w[l] = d.shape[2], d.shape[3]
+        sa.disp[l], sa.img[l] = d.data_ptr(), img.data_ptr()
+        if need_grad:
+            g = torch.empty_like(d)
+            gsm.append(g)
+            sa.gdisp[l] = g.data_ptr()
+    hs = (C.c_int32 * S)(*[d.shape[2] for d in disps_c])
+    ws = (C.c_int32 * S)(*[d.shape[3] for d in disps_c])
+    scratch = torch.empty(max(1, be.value("smooth_scratch_floats", B, S, hs, ws)), **f32)
+    smooth = torch.empty(S, **f32)
+    sa.scratch, sa.loss = scratch.data_ptr(), smooth.data_ptr()
+    keep.append(scratch)
+
+    join = None
+    if be.cuda:
+        main, side = torch.cuda.current_stream(), _side_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            be.call("disp_to_depth_forward", C.byref(d2d))
+            be.call("smooth_fused", C.byref(sa))
+            join = torch.cuda.Event()
+            join.record(side)
+            # (joining the smoothness kernels only after the fused kernel was measured: their tail then
+            # competes with its first waves and costs it 9 us -- no net gain)
+    else:
+        be.call("disp_to_depth_forward", C.byref(d2d))
+        be.call("smooth_fused", C.byref(sa))
+    return dict(disps=disps_key(disps), disps_c=disps_c, d2d=d2d, depth=depth, gsm=gsm, smooth=smooth, join=join,
+                keep=keep)
+
+
 class _FusedLoss(torch.autograd.Function):
     """(P, disp_0..disp_{S-1}) -> (reproj[S], smooth[S]); everything else is closed over."""
 
@@ -81,63 +152,22 @@ class _FusedLoss(torch.autograd.Function):
         assert plan.batch == B and P.shape == (plan.n_pose, 3, 4), (P.shape, plan.n_pose)
         assert S <= _lib.MAX_SCALES
 
-        disps_c = [d.detach().contiguous() for d in disps]
         Pc = P.detach().contiguous()
         target = target.contiguous()
         inv_K = inv_K.contiguous()
         tab = _tables(plan, dev)
         frame_arr, keep = _frame_ptrs(plan, frames, H, W)
 
-        # 1. disparity -> depth at full resolution for every scale
-        depth = torch.empty(S, B, H, W, **f32)
-        d2d = _lib.D2DArgs()
-        d2d.batch, d2d.levels, d2d.height, d2d.width = B, S, H, W
-        d2d.min_disp = 1 / cfg["max_depth"]
-        d2d.disp_span = 1 / cfg["min_depth"] - 1 / cfg["max_depth"]
-        d2d.sql = int(cfg["sql"])
-        for l, d in enumerate(disps_c):
-            d2d.h[l], d2d.w[l] = d.shape[2], d.shape[3]
-            d2d.disp[l] = d.data_ptr()
-        d2d.depth = depth.data_ptr()
-
-        # 5 (prepared here, see below). smoothness on the disparity pyramid
-        sa = _lib.SmoothArgs()
-        sa.batch, sa.levels, sa.normalize = B, S, 1
-        gsm = []
-        smooth_src = disps_c
-        for l, d in enumerate(smooth_src):
-            img = pyramid[l].contiguous()
-            keep.append(img)
-            assert img.shape[0] == B and img.shape[-2:] == d.shape[-2:], (img.shape, d.shape)
-            sa.h[l], sa.w[l] = d.shape[2], d.shape[3]
-            sa.disp[l], sa.img[l] = d.data_ptr(), img.data_ptr()
-            if need_grad:
-                g = torch.empty_like(d)
-                gsm.append(g)
-                sa.gdisp[l] = g.data_ptr()
-        hs = (C.c_int32 * S)(*[d.shape[2] for d in smooth_src])
-        ws = (C.c_int32 * S)(*[d.shape[3] for d in smooth_src])
-        scratch = torch.empty(max(1, be.value("smooth_scratch_floats", B, S, hs, ws)), **f32)
-        smooth = torch.empty(S, **f32)
-        sa.scratch, sa.loss = scratch.data_ptr(), smooth.data_ptr()
-
-        # Steps 1 and 5 depend only on the disparities and the colour pyramid.  Every buffer they write
-        # was allocated above on the launch stream, so they can run on the helper stream between a
-        # fork and a join event while the identity pre-pass (step 2) runs here.
-        join = None
-        if be.cuda:
-            main, side = torch.cuda.current_stream(), _side_stream(dev)
-            fork = torch.cuda.Event()
-            fork.record(main)
-            side.wait_event(fork)
-            with torch.cuda.stream(side):
-                be.call("disp_to_depth_forward", C.byref(d2d))
-                be.call("smooth_fused", C.byref(sa))
-                join = torch.cuda.Event()
-                join.record(side)
-        else:
-            be.call("disp_to_depth_forward", C.byref(d2d))
-            be.call("smooth_fused", C.byref(sa))
+        # 1 + 5. disparity -> depth and smoothness: on the helper stream (started here unless the caller
+        # already did, see start_side_branch)
+        # (popped: `smooth` becomes an output of this node, and an output reachable from ctx would be a
+        # reference cycle that keeps the autograd graph -- and its AccumulateGrad nodes -- alive)
+        pre = cfg.pop("pre", None)
+        if pre is None or pre["disps"] != disps_key(disps) or (need_grad and not pre["gsm"]):
+            pre = start_side_branch(be, disps, pyramid, (B, H, W), cfg["min_depth"], cfg["max_depth"], cfg["sql"],
+                                    need_grad)
+        disps_c, d2d, depth, gsm, smooth, join = (pre[k] for k in ("disps_c", "d2d", "depth", "gsm", "smooth", "join"))
+        keep.extend(pre["keep"])
 
         # 2. identity pre-pass (once per step)
         ident_min = torch.empty(B, H, W, **f32)
@@ -224,7 +254,7 @@ def fused_losses(plan: LossPlan, target: torch.Tensor, frames: Dict, disps: Sequ
                  inv_K: torch.Tensor, P: torch.Tensor, noise: Dict, pyramid: Sequence[torch.Tensor], *,
                  min_depth=0.1, max_depth=100.0, no_ssim=False, sql=False, noise_scale=1.0,
                  want_winner=False, need_grad: Optional[bool] = None, backend: Optional[_lib.Backend] = None,
-                 timers: Optional[dict] = None):
+                 timers: Optional[dict] = None, pre: Optional[dict] = None):
     """Per-scale ``(reproj[S], smooth[S], aux)`` of the view-synthesis loss.
 
     ``frames[f]`` are the compacted ``("color", f, 0)`` stacks, ``disps[s]`` the network
@@ -238,9 +268,47 @@ def fused_losses(plan: LossPlan, target: torch.Tensor, frames: Dict, disps: Sequ
         need_grad = torch.is_grad_enabled() and (P.requires_grad or any(d.requires_grad for d in disps))
     cfg = dict(backend=be, plan=plan, target=target, frames=frames, inv_K=inv_K, noise=noise,
                pyramid=list(pyramid), min_depth=min_depth, max_depth=max_depth, no_ssim=no_ssim, sql=sql,
-               noise_scale=noise_scale, want_winner=want_winner, need_grad=need_grad, timers=timers)
+               noise_scale=noise_scale, want_winner=want_winner, need_grad=need_grad, timers=timers, pre=pre)
     reproj, smooth = _FusedLoss.apply(cfg, P, *disps)
     return reproj, smooth, cfg["aux"]
+
+
+class _Combine(torch.autograd.Function):
+    """(reproj[S], smooth[S]) -> (per_scale[S], total): the loss assembly of ``trainer.py:557-570`` as one
+    launch each way instead of ~10 four-element tensor kernels."""
+
+    @staticmethod
+    def forward(ctx, reproj, smooth, weight, num_scales, be):
+        S = reproj.shape[0]
+        r, m = reproj.detach().contiguous(), smooth.detach().contiguous()
+        be.check_device(r, m, weight)
+        out = torch.empty(S + 1, device=r.device, dtype=torch.float32)   # [per_scale..., total]
+        per_scale, total = out[:S], out[S]
+        be.call("loss_combine_forward", S, C.c_void_p(r.data_ptr()), C.c_void_p(m.data_ptr()),
+                C.c_void_p(weight.data_ptr()), C.c_float(float(num_scales)), C.c_void_p(out.data_ptr()),
+                C.c_void_p(out.data_ptr() + 4 * S))
+        ctx.weight, ctx.num_scales, ctx.be, ctx.S = weight, float(num_scales), be, S
+        ctx.set_materialize_grads(False)    # an unused output arrives as None, not as a zero tensor
+        return per_scale, total
+
+    @staticmethod
+    def backward(ctx, g_per_scale, g_total):
+        S, be = ctx.S, ctx.be
+        if g_per_scale is None and g_total is None:
+            return None, None, None, None, None
+        gps = g_per_scale.contiguous().float() if g_per_scale is not None else None
+        gt = g_total.contiguous().float() if g_total is not None else None
+        g = torch.empty(2, S, device=ctx.weight.device, dtype=torch.float32)
+        be.call("loss_combine_backward", S, C.c_void_p(_lib.ptr(gt)), C.c_void_p(_lib.ptr(gps)),
+                C.c_void_p(ctx.weight.data_ptr()), C.c_float(ctx.num_scales), C.c_void_p(g.data_ptr()),
+                C.c_void_p(g.data_ptr() + 4 * S))
+        return g[0], g[1], None, None, None
+
+
+def combine_losses(reproj, smooth, weight, num_scales, backend: Optional[_lib.Backend] = None):
+    """``per_scale[s] = reproj[s] + weight[s] * smooth[s]``, ``total = sum(per_scale) / num_scales``."""
+    be = backend if backend is not None else _lib.cuda_backend()
+    return _Combine.apply(reproj, smooth, weight, num_scales, be)
 
 
 class _PosePack(torch.autograd.Function):

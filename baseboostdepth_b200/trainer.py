@@ -29,7 +29,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib
-from .fused import _PosePack, fused_losses, pack_poses
+from .fused import _PosePack, combine_losses, fused_losses, pack_poses, start_side_branch
 from .plan import LossPlan, build_plan
 
 _PLAN_CACHE: Dict = {}
@@ -108,16 +108,22 @@ def loss_step(inputs, outputs, opt, plan: Optional[LossPlan] = None, noise=None,
     scales = list(opt.scales)
     num_scales = num_scales if num_scales is not None else len(scales)
 
-    T = _frame_poses(plan, inputs, outputs, "cam_T_cam", row_masks)
-    T_err = _frame_poses(plan, inputs, outputs, "cam_T_cam_error", row_masks) if plan.decomp else None
-    P = pack_poses(plan, inputs[("K", 0)], T, T_err, backend=backend)
-    frames = {f: inputs[("color", f, 0)] for f in plan.frames}
     disps = [outputs[("disp", s)] for s in scales]
     pyramid = [inputs[("color", 0, s)] for s in scales]
     if getattr(opt, "SQL", False):
         for d, c in zip(disps, pyramid):
             if d.shape[-2:] != c.shape[-2:]:
                 raise NotImplementedError("opt.SQL with a disparity pyramid smaller than its colour level")
+    # disparity -> depth and the smoothness kernels start first, on the helper stream; the pose packing,
+    # the noise draw and the identity pre-pass below run next to them
+    be = backend if backend is not None else _lib.cuda_backend()
+    pre = start_side_branch(be, disps, pyramid, (B, H, W), opt.min_depth, opt.max_depth, getattr(opt, "SQL", False),
+                            torch.is_grad_enabled())
+
+    T = _frame_poses(plan, inputs, outputs, "cam_T_cam", row_masks)
+    T_err = _frame_poses(plan, inputs, outputs, "cam_T_cam_error", row_masks) if plan.decomp else None
+    P = pack_poses(plan, inputs[("K", 0)], T, T_err, backend=backend)
+    frames = {f: inputs[("color", f, 0)] for f in plan.frames}
     if noise is None:
         noise, noise_scale = draw_noise(plan, H, W, color0.device), 0.00001
     else:
@@ -127,12 +133,12 @@ def loss_step(inputs, outputs, opt, plan: Optional[LossPlan] = None, noise=None,
         plan, color0, frames, disps, inputs[("inv_K", 0)], P, noise, pyramid,
         min_depth=opt.min_depth, max_depth=opt.max_depth, no_ssim=opt.no_ssim,
         sql=getattr(opt, "SQL", False), noise_scale=noise_scale, want_winner=want_winner, backend=backend,
-        timers=timers)
+        timers=timers, pre=pre)
 
     weights = _weights(tuple(opt.disparity_smoothness / (2 ** s) for s in scales), reproj.device)
-    per_scale = reproj + weights * smooth
+    per_scale, total = combine_losses(reproj, smooth, weights, num_scales, backend=backend)
     losses = {f"loss/{s}": per_scale[i] for i, s in enumerate(scales)}
-    losses["loss"] = per_scale.sum() / num_scales
+    losses["loss"] = total
     for i, s in enumerate(scales):
         outputs[("depth", 0, s)] = aux["depth"][i].unsqueeze(1)
     if want_winner:

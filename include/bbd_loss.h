@@ -217,6 +217,16 @@ int bbd_ssim_forward(int32_t n, int32_t channels, int32_t height, int32_t width,
 int bbd_ssim_backward(int32_t n, int32_t channels, int32_t height, int32_t width, const float* x,
                       const float* y, const float* gout, float* gx, float* gy, bbd_stream_t stream);
 
+/* Loss assembly, trainer.py:557-570: per_scale[s] = reproj[s] + weight[s] * smooth[s]
+ * (weight[s] = disparity_smoothness / 2^s), total = (((p0 + p1) + p2) + ...) / num_scales -- one launch
+ * instead of a handful of 4-element tensor kernels.  backward: g_total (1 float, may be NULL),
+ * g_per_scale (S floats, may be NULL) -> g_reproj[S], g_smooth[S] (the upstream scalars the fused
+ * loss's backward consumes).  All pointers are device memory. */
+int bbd_loss_combine_forward(int32_t num_terms, const float* reproj, const float* smooth, const float* weight,
+                             float num_scales, float* per_scale, float* total, bbd_stream_t stream);
+int bbd_loss_combine_backward(int32_t num_terms, const float* g_total, const float* g_per_scale, const float* weight,
+                              float num_scales, float* g_reproj, float* g_smooth, bbd_stream_t stream);
+
 /* Frames as decoded (8-bit) -> the fp32 tensors the reference's loader hands the trainer:
  * torchvision ToTensor = uint8 -> float32, IEEE division by 255 (datasets/mono_dataset.py:55,201-203).
  * dst[i] = (float)src[i] / 255 for i < n, bit-identical to ToTensor.  Lets a batch cross PCIe at

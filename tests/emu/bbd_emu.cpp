@@ -341,6 +341,17 @@ int emu_ssim_backward(int32_t n, int32_t ch, int32_t H, int32_t W, const float* 
   return 0;
 }
 
+int emu_loss_combine_forward(int32_t n, const float* reproj, const float* smooth, const float* weight, float num_scales,
+                             float* per_scale, float* total) {
+  loss_combine(n, reproj, smooth, weight, num_scales, per_scale, total);
+  return 0;
+}
+int emu_loss_combine_backward(int32_t n, const float* g_total, const float* g_per_scale, const float* weight,
+                              float num_scales, float* g_reproj, float* g_smooth) {
+  loss_combine_grad(n, g_total, g_per_scale, weight, num_scales, g_reproj, g_smooth);
+  return 0;
+}
+
 int emu_u8_to_f32(const uint8_t* src, float* dst, size_t n) {
   for (size_t i = 0; i < n; ++i) dst[i] = u8_to_unit(src[i]);
   return 0;

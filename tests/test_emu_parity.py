@@ -120,3 +120,22 @@ def test_sql_mode_emulated():
         res.append((float(losses["loss"]), params[("disp", 0)].grad.clone()))
     assert abs(res[0][0] - res[1][0]) <= 2e-6
     assert rel_l2(res[1][1], res[0][1]) <= 1e-5
+
+
+def test_step_leaves_no_reference_cycle():
+    """The autograd graph of a step must die with its loss (refcount, no GC): a cycle through the fused
+    node keeps AccumulateGrad nodes alive across steps, which breaks CUDA-graph capture later."""
+    import gc
+    import weakref
+    g = Golden("plain_pm1")
+    gc.collect()
+    gc.disable()
+    try:
+        losses, _ = run_fused(g.inputs, g.outputs, g.opt(), g.noise, g.num_scales, backend=emu_backend())
+        node = losses["loss"].grad_fn
+        nodes = [node] + [fn for fn, _ in node.next_functions if fn is not None]
+        refs = [weakref.ref(n) for n in nodes]
+        del losses, node, nodes
+        assert all(r() is None for r in refs)
+    finally:
+        gc.enable()
