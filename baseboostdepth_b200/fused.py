@@ -27,12 +27,13 @@ from .plan import LossPlan
 _SIDE: Dict = {}
 
 
-def _side_stream(device):
-    """One helper stream per device: the disparity -> depth and smoothness kernels (small, latency-bound)
-    run on it next to the identity pre-pass and join the launch stream before the fused kernel."""
+def _side_streams(device):
+    """Two helper streams per device: the disparity -> depth kernel on one, the smoothness kernels on the
+    other (all small and latency-bound) run next to the identity pre-pass and join the launch stream
+    before the fused kernel."""
     s = _SIDE.get(device)
     if s is None:
-        s = _SIDE[device] = torch.cuda.Stream(device=device)
+        s = _SIDE[device] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
     return s
 
 
@@ -116,17 +117,19 @@ def start_side_branch(be, disps, pyramid, bhw, min_depth, max_depth, sql, need_g
 
     join = None
     if be.cuda:
-        main, side = torch.cuda.current_stream(), _side_stream(dev)
+        main, (side_a, side_b) = torch.cuda.current_stream(), _side_streams(dev)
         fork = torch.cuda.Event()
         fork.record(main)
-        side.wait_event(fork)
-        with torch.cuda.stream(side):
-            be.call("disp_to_depth_forward", C.byref(d2d))
-            be.call("smooth_fused", C.byref(sa))
-            join = torch.cuda.Event()
-            join.record(side)
-            # (joining the smoothness kernels only after the fused kernel was measured: their tail then
-            # competes with its first waves and costs it 9 us -- no net gain)
+        join = []
+        for side, name, args in ((side_a, "smooth_fused", sa), (side_b, "disp_to_depth_forward", d2d)):
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                be.call(name, C.byref(args))
+                ev = torch.cuda.Event()
+                ev.record(side)
+                join.append(ev)
+        # (joining the smoothness kernels only after the fused kernel was measured: their tail then
+        # competes with its first waves and costs it 9 us -- no net gain)
     else:
         be.call("disp_to_depth_forward", C.byref(d2d))
         be.call("smooth_fused", C.byref(sa))
@@ -187,8 +190,8 @@ class _FusedLoss(torch.autograd.Function):
         ia.ident_min = ident_min.data_ptr()
         ia.ident_arg = _lib.ptr(ident_arg)
         be.call("ident_forward", C.byref(ia))
-        if join is not None:
-            torch.cuda.current_stream().wait_event(join)
+        for ev in join or ():
+            torch.cuda.current_stream().wait_event(ev)
 
         # 3. fused warp + photometric + min (+ gradients)
         ntiles = be.value("reproj_tiles", H, W)
