@@ -57,7 +57,8 @@ class D2DArgs(C.Structure):
 EXPORTS = [
     "bbd_version", "bbd_last_error_string", "bbd_reproj_tiles", "bbd_ident_forward", "bbd_reproj_fused",
     "bbd_reproj_finalize", "bbd_warp_forward", "bbd_smooth_scratch_floats", "bbd_smooth_fused",
-    "bbd_disp_to_depth_forward", "bbd_disp_to_depth_backward", "bbd_d2d_scratch_floats", "bbd_backproject_forward",
+    "bbd_disp_to_depth_forward", "bbd_disp_to_depth_backward", "bbd_disp_to_depth_backward_pass1",
+    "bbd_disp_to_depth_backward_pass2", "bbd_d2d_scratch_floats", "bbd_backproject_forward",
     "bbd_backproject_backward", "bbd_project_forward", "bbd_project_chunks", "bbd_project_backward",
     "bbd_ssim_forward", "bbd_ssim_backward", "bbd_pose_pack_forward", "bbd_pose_pack_backward",
     "bbd_pose_forward", "bbd_pose_backward", "bbd_grid_sample_forward", "bbd_grid_sample_backward",

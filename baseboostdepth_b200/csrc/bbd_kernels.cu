@@ -345,8 +345,8 @@ __global__ void __launch_bounds__(128) d2d_hpass_kernel(const bbd_d2d_args a) {
 }
 
 // grid (column blocks, rows, levels): rows are (b, iy) of the level's own resolution
-__global__ void __launch_bounds__(128) d2d_backward_kernel(const bbd_d2d_args a) {
-  const int lvl = blockIdx.z;
+__global__ void __launch_bounds__(128) d2d_backward_kernel(const bbd_d2d_args a, int level_begin) {
+  const int lvl = blockIdx.z + level_begin;
   const int h = a.h[lvl], w = a.w[lvl];
   const int ix = blockIdx.x * blockDim.x + threadIdx.x;
   if (ix >= w) return;
@@ -594,7 +594,7 @@ int bbd_disp_to_depth_forward(const bbd_d2d_args* a, bbd_stream_t stream) {
   return check_launch("d2d_forward_kernel");
 }
 
-int bbd_disp_to_depth_backward(const bbd_d2d_args* a, bbd_stream_t stream) {
+static int d2d_backward_check(const bbd_d2d_args* a) {
   if (!a || !a->depth || !a->gdepth || !a->gscale) return fail(BBD_E_ARG, "d2d backward: null argument");
   if (a->levels < 1 || a->levels > BBD_MAX_SCALES) return fail(BBD_E_RANGE, "d2d: bad level count");
   for (int l = 0; l < a->levels; ++l) {
@@ -602,21 +602,40 @@ int bbd_disp_to_depth_backward(const bbd_d2d_args* a, bbd_stream_t stream) {
     if (a->height % a->h[l] || a->width % a->w[l] || a->height / a->h[l] > 8 || a->width / a->w[l] > 8)
       return fail(BBD_E_RANGE, "d2d backward: scale factor must be an integer <= 8");
   }
+  return 0;
+}
+
+int bbd_disp_to_depth_backward_pass1(const bbd_d2d_args* a, bbd_stream_t stream) {
+  if (int rc = d2d_backward_check(a)) return rc;
+  if (!a->scratch) return 0;
+  int wsep = 0;
+  for (int l = 0; l < a->levels; ++l)
+    if (d2d_sep_factor(*a, l)) wsep = std::max(wsep, a->w[l]);
+  if (!wsep) return 0;
+  const size_t rows = (size_t)a->batch * a->height;
+  dim3 hgrid((unsigned)((wsep + 127) / 128), (unsigned)std::min<size_t>(rows, kRowBlocks), a->levels);
+  d2d_hpass_kernel<<<hgrid, 128, 0, (cudaStream_t)stream>>>(*a);
+  return check_launch("d2d_hpass_kernel");
+}
+
+int bbd_disp_to_depth_backward_pass2(const bbd_d2d_args* a, int32_t level_begin, int32_t level_end, bbd_stream_t stream) {
+  if (int rc = d2d_backward_check(a)) return rc;
+  if (level_begin < 0 || level_end > a->levels || level_begin > level_end) return fail(BBD_E_RANGE, "d2d backward: bad level range");
+  if (level_begin == level_end) return 0;
   int wmax = 1, hmax = 1;
-  for (int l = 0; l < a->levels; ++l) {
+  for (int l = level_begin; l < level_end; ++l) {
     wmax = std::max(wmax, a->w[l]);
     hmax = std::max(hmax, a->h[l]);
   }
-  const unsigned cols = (unsigned)((wmax + 127) / 128);
-  if (a->scratch) {
-    const size_t rows = (size_t)a->batch * a->height;
-    dim3 hgrid(cols, (unsigned)std::min<size_t>(rows, kRowBlocks), a->levels);
-    d2d_hpass_kernel<<<hgrid, 128, 0, (cudaStream_t)stream>>>(*a);
-  }
   const size_t rows = (size_t)a->batch * hmax;
-  dim3 grid(cols, (unsigned)std::min<size_t>(rows, kRowBlocks), a->levels);
-  d2d_backward_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*a);
+  dim3 grid((unsigned)((wmax + 127) / 128), (unsigned)std::min<size_t>(rows, kRowBlocks), level_end - level_begin);
+  d2d_backward_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*a, level_begin);
   return check_launch("d2d_backward_kernel");
+}
+
+int bbd_disp_to_depth_backward(const bbd_d2d_args* a, bbd_stream_t stream) {
+  if (int rc = bbd_disp_to_depth_backward_pass1(a, stream)) return rc;
+  return bbd_disp_to_depth_backward_pass2(a, 0, a->levels, stream);
 }
 
 size_t bbd_d2d_scratch_floats(const bbd_d2d_args* a) {

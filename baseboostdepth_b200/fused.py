@@ -249,7 +249,24 @@ class _FusedLoss(torch.autograd.Function):
         scratch = torch.empty(max(1, be.value("d2d_scratch_floats", C.byref(d2d))), device=gdepth.device,
                               dtype=torch.float32)
         d2d.scratch = scratch.data_ptr()
-        be.call("disp_to_depth_backward", C.byref(d2d))
+        S = len(gdisps)
+        full_res_first = S > 1 and tuple(disps_c[0].shape[-2:]) == tuple(depth.shape[-2:])
+        if be.cuda and full_res_first:
+            # pass 2 of a full-resolution level does not read the row sums of pass 1: it runs on a helper
+            # stream next to pass 1, the remaining levels follow pass 1 on this stream
+            main, (side, _) = torch.cuda.current_stream(), _side_streams(gdepth.device)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                be.call("disp_to_depth_backward_pass2", C.byref(d2d), 0, 1)
+                join = torch.cuda.Event()
+                join.record(side)
+            be.call("disp_to_depth_backward_pass1", C.byref(d2d))
+            be.call("disp_to_depth_backward_pass2", C.byref(d2d), 1, S)
+            main.wait_event(join)
+        else:
+            be.call("disp_to_depth_backward", C.byref(d2d))
         return (None, gP) + tuple(gdisps)
 
 

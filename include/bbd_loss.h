@@ -184,6 +184,14 @@ typedef struct bbd_d2d_args {
 size_t bbd_d2d_scratch_floats(const bbd_d2d_args* a);
 int bbd_disp_to_depth_forward(const bbd_d2d_args* a, bbd_stream_t stream);
 int bbd_disp_to_depth_backward(const bbd_d2d_args* a, bbd_stream_t stream);
+/* The two passes of bbd_disp_to_depth_backward on their own, for callers that overlap them on streams:
+ * pass 1 reduces gdepth along rows into `scratch` for the levels with an integer factor 2/4/8 (it needs
+ * neither the upstream scalars nor the smoothness gradient); pass 2 finishes the levels
+ * [level_begin, level_end) -- a level at full resolution does not read `scratch`, so its pass 2 can run
+ * next to pass 1. */
+int bbd_disp_to_depth_backward_pass1(const bbd_d2d_args* a, bbd_stream_t stream);
+int bbd_disp_to_depth_backward_pass2(const bbd_d2d_args* a, int32_t level_begin, int32_t level_end,
+                                     bbd_stream_t stream);
 
 /* ---- module-level operators (tier A: trainer.py unchanged) -----------------
  * Same maths as the layers in layers.py, one kernel each, forward and backward. */

@@ -239,7 +239,7 @@ int emu_disp_to_depth_forward(const bbd_d2d_args* ap) {
 
 size_t emu_d2d_scratch_floats(const bbd_d2d_args* a) { return d2d_scratch_offset(*a, a->levels); }
 
-int emu_disp_to_depth_backward(const bbd_d2d_args* ap) {
+int emu_disp_to_depth_backward_pass1(const bbd_d2d_args* ap) {
   const bbd_d2d_args& a = *ap;
   if (a.scratch)
     for (int lvl = 0; lvl < a.levels; ++lvl) {
@@ -252,13 +252,23 @@ int emu_disp_to_depth_backward(const bbd_d2d_args* ap) {
         tmp[i] = f == 2 ? d2d_hpass<2>(a, lvl, b, oy, ix) : (f == 4 ? d2d_hpass<4>(a, lvl, b, oy, ix) : d2d_hpass<8>(a, lvl, b, oy, ix));
       }
     }
-  for (int lvl = 0; lvl < a.levels; ++lvl) {
+  return 0;
+}
+
+int emu_disp_to_depth_backward_pass2(const bbd_d2d_args* ap, int32_t level_begin, int32_t level_end) {
+  const bbd_d2d_args& a = *ap;
+  for (int lvl = level_begin; lvl < level_end; ++lvl) {
     const int h = a.h[lvl], w = a.w[lvl];
     const float sy = (float)h / (float)a.height, sx = (float)w / (float)a.width;
     for (int b = 0; b < a.batch; ++b)
       for (int i = 0; i < h * w; ++i) a.gdisp[lvl][(size_t)b * h * w + i] = d2d_backward_px(a, lvl, b, i / w, i % w, sy, sx);
   }
   return 0;
+}
+
+int emu_disp_to_depth_backward(const bbd_d2d_args* ap) {
+  emu_disp_to_depth_backward_pass1(ap);
+  return emu_disp_to_depth_backward_pass2(ap, 0, ap->levels);
 }
 
 int emu_pose_forward(int32_t n, const float* aa, const float* tr, int32_t invert, float* T) {
