@@ -89,6 +89,18 @@ BBD_HD float d2d_hpass(const bbd_d2d_args& a, int lvl, int b, int oy, int ix) {
   const float nspan = -a.disp_span;
   const int ox0 = ix * F - F / 2;
   float acc = 0.0f;
+  if (ix > 0 && ix < w - 1) {
+    // interior column: all 2F taps are inside the row and carry the plain tent weights (constants)
+    const float* g = gd + ox0;
+    const float* dp = dep + ox0;
+#pragma unroll
+    for (int k = 0; k < 2 * F; ++k) {
+      float v = g[k];
+      if (!a.sql) { const float d = dp[k]; v *= nspan * d * d; }
+      acc += d2d_tent<F>(k - F / 2, 1, 3) * v;
+    }
+    return acc;
+  }
 #pragma unroll
   for (int k = 0; k < 2 * F; ++k) {
     const int ox = ox0 + k;
@@ -106,6 +118,12 @@ BBD_HD float d2d_vpass(const bbd_d2d_args& a, int lvl, int b, int iy, int ix) {
   const float* tmp = a.scratch + d2d_scratch_offset(a, lvl) + (size_t)b * H * w;
   const int oy0 = iy * F - F / 2;
   float acc = 0.0f;
+  if (iy > 0 && iy < h - 1) {  // interior row: plain tent weights, no bounds checks
+    const float* col = tmp + (size_t)oy0 * w + ix;
+#pragma unroll
+    for (int k = 0; k < 2 * F; ++k) acc += d2d_tent<F>(k - F / 2, 1, 3) * col[(size_t)k * w];
+    return acc;
+  }
 #pragma unroll
   for (int k = 0; k < 2 * F; ++k) {
     const int oy = oy0 + k;
