@@ -384,3 +384,36 @@ def test_sql_mode_matches_oracle(cuda_device):
     losses["loss"].backward()
     assert abs(float(losses["loss"]) - float(ref["loss"])) <= 2e-6
     assert rel_l2(leaves[("disp", 0)].grad, params[("disp", 0)].grad) <= 1e-5
+
+
+def test_depth_planes_against_aten_cpu_and_cuda(cuda_device):
+    """disparity -> depth at the benchmark size: bit-identical to the reference's ops on the CPU
+    (F.interpolate + disp_to_depth, trainer.py:456-460) and within one ulp of the same ops run by ATen's
+    CUDA kernels (what the reference launches on a GPU; its upsample kernel contracts differently)."""
+    import ctypes as C
+    import torch.nn.functional as F
+    from baseboostdepth_b200 import _lib
+    be = _lib.cuda_backend()
+    B, H, W, S = 2, 192, 640, 4
+    gen = torch.Generator().manual_seed(5)
+    disps = [0.01 + 0.3 * torch.rand(B, 1, H >> s, W >> s, generator=gen) for s in range(S)]
+    dev_disps = [d.to(cuda_device) for d in disps]
+    a = _lib.D2DArgs()
+    a.batch, a.levels, a.height, a.width = B, S, H, W
+    a.min_disp, a.disp_span, a.sql = 1 / 100.0, 1 / 0.1 - 1 / 100.0, 0
+    depth = torch.empty(S, B, H, W, device=cuda_device)
+    for l, d in enumerate(dev_disps):
+        a.h[l], a.w[l], a.disp[l] = d.shape[2], d.shape[3], d.data_ptr()
+    a.depth = depth.data_ptr()
+    be.call("disp_to_depth_forward", C.byref(a))
+    torch.cuda.synchronize()
+
+    def reference(d):
+        up = F.interpolate(d, [H, W], mode="bilinear", align_corners=False)
+        return (1 / (1 / 100.0 + (1 / 0.1 - 1 / 100.0) * up))[:, 0]
+
+    for l in range(S):
+        assert torch.equal(depth[l].cpu(), reference(disps[l])), l
+        on_gpu = reference(dev_disps[l])
+        rel = ((depth[l] - on_gpu).abs() / on_gpu.abs()).max().item()
+        assert rel <= 2.5e-7, (l, rel)

@@ -224,3 +224,70 @@ def test_u8_to_f32_is_totensor():
     dst = torch.empty(src.numel(), dtype=torch.float32)
     be.call("u8_to_f32", ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()), ctypes.c_size_t(src.numel()))
     assert torch.equal(dst, src.to(torch.float32).div(255))
+
+
+@pytest.mark.parametrize("sizes", [((24, 40), [(24, 40), (12, 20), (6, 10), (3, 5)]),
+                                   ((16, 24), [(8, 12), (2, 3)]),
+                                   ((64, 96), [(64, 96), (32, 48), (16, 24), (8, 12)])])
+def test_disp_to_depth_against_autograd(sizes):
+    """bbd_disp_to_depth_forward/backward (and the two backward passes on their own) vs
+    F.interpolate(bilinear, align_corners=False) + disp_to_depth under autograd (trainer.py:456-460)."""
+    import ctypes as C
+    import torch.nn.functional as F
+    from baseboostdepth_b200 import _lib
+    be = emu_backend()
+    (H, W), levels = sizes
+    B, S = 2, len(levels)
+    gen = torch.Generator().manual_seed(3)
+    disps = [(0.01 + 0.3 * torch.rand(B, 1, h, w, generator=gen)).requires_grad_(True) for h, w in levels]
+    gdepth = torch.randn(S, B, H, W, generator=gen)
+    gscale = torch.rand(S, generator=gen) + 0.5
+    min_disp, span = 1 / 100.0, 1 / 0.1 - 1 / 100.0
+
+    want_depth, want_grads = [], []
+    for l, d in enumerate(disps):
+        up = F.interpolate(d, [H, W], mode="bilinear", align_corners=False)
+        depth = 1 / (min_disp + span * up)
+        want_depth.append(depth.detach()[:, 0])
+        (depth[:, 0] * gdepth[l] * gscale[l]).sum().backward()
+        want_grads.append(d.grad.clone())
+
+    a = _lib.D2DArgs()
+    a.batch, a.levels, a.height, a.width = B, S, H, W
+    a.min_disp, a.disp_span, a.sql = min_disp, span, 0
+    depth = torch.empty(S, B, H, W)
+    cont = [d.detach().contiguous() for d in disps]
+    for l, d in enumerate(cont):
+        a.h[l], a.w[l], a.disp[l] = d.shape[2], d.shape[3], d.data_ptr()
+    a.depth = depth.data_ptr()
+    be.call("disp_to_depth_forward", C.byref(a))
+    for l in range(S):
+        # ATen's CPU upsample has two code paths: from 64x96 outputs on (the sizes that matter) the kernel
+        # reproduces it bit for bit; for tiny outputs ATen rounds its lerps differently by one ulp
+        if H * W >= 64 * 96:
+            assert torch.equal(depth[l], want_depth[l]), l
+        else:
+            assert float(((depth[l] - want_depth[l]).abs() / want_depth[l].abs()).max()) <= 5e-7, l
+
+    def backward(split):
+        out = [torch.full_like(d, float("nan")) for d in cont]
+        a.gdepth, a.gscale = gdepth.data_ptr(), gscale.data_ptr()
+        for l, g in enumerate(out):
+            a.gdisp[l] = g.data_ptr()
+        scratch = torch.empty(max(1, be.value("d2d_scratch_floats", C.byref(a))))
+        a.scratch = scratch.data_ptr()
+        if split:
+            be.call("disp_to_depth_backward_pass2", C.byref(a), 0, 1)   # a full-resolution level needs no pass 1
+            be.call("disp_to_depth_backward_pass1", C.byref(a))
+            be.call("disp_to_depth_backward_pass2", C.byref(a), 1, S)
+        else:
+            be.call("disp_to_depth_backward", C.byref(a))
+        return out
+
+    whole = backward(False)
+    for l in range(S):
+        assert rel_l2(whole[l], want_grads[l]) <= 2e-6, (l, rel_l2(whole[l], want_grads[l]))
+    if levels[0] == (H, W):
+        parts = backward(True)
+        for l in range(S):
+            assert torch.equal(parts[l], whole[l]), l
