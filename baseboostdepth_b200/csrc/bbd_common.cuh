@@ -247,10 +247,20 @@ struct SsimParts {
   float mux, sigx, sigxy, n1, n2, d1, d2, r, raw;
 };
 
+// ... from the window moments (mean, variance term, covariance term) of the warped image
+BBD_HD float ssim_from_moments(float mux, float sigx, float sigxy, const WinY& wy, SsimParts& q);
+
 BBD_HD float ssim_channel(const WinX& wx, const WinY& wy, SsimParts& q) {
-  q.mux = ninth(wx.sx);
-  q.sigx = sub(ninth(wx.sxx), mul(q.mux, q.mux));
-  q.sigxy = sub(ninth(wx.sxy), mul(q.mux, wy.mu));
+  const float mux = ninth(wx.sx);
+  const float sigx = sub(ninth(wx.sxx), mul(mux, mux));
+  const float sigxy = sub(ninth(wx.sxy), mul(mux, wy.mu));
+  return ssim_from_moments(mux, sigx, sigxy, wy, q);
+}
+
+BBD_HD float ssim_from_moments(float mux, float sigx, float sigxy, const WinY& wy, SsimParts& q) {
+  q.mux = mux;
+  q.sigx = sigx;
+  q.sigxy = sigxy;
   q.n1 = add(mul(mul(2.0f, q.mux), wy.mu), BBD_C1);
   q.n2 = add(mul(2.0f, q.sigxy), BBD_C2);
   q.d1 = add(add(mul(q.mux, q.mux), mul(wy.mu, wy.mu)), BBD_C1);
@@ -262,10 +272,12 @@ BBD_HD float ssim_channel(const WinX& wx, const WinY& wy, SsimParts& q) {
 
 // Two window centres at once (same operation order, hence bit-identical to ssim_channel).
 BBD_HD f2 ninth(const f2& s) { return div_const(s, 9.0f, 0.111111111938953399658203125f); }
-BBD_HD f2 ssim_channel2(const f2& sx, const f2& sxx, const f2& sxy, const f2& muy, const f2& sigy) {
-  const f2 mux = ninth(sx);
-  const f2 sigx = sub(ninth(sxx), mul(mux, mux));
-  const f2 sigxy = sub(ninth(sxy), mul(mux, muy));
+// (also hands back the window moments, which is what the winner selection keeps for the backward)
+BBD_HD f2 ssim_channel2(const f2& sx, const f2& sxx, const f2& sxy, const f2& muy, const f2& sigy, f2& mux, f2& sigx,
+                        f2& sigxy) {
+  mux = ninth(sx);
+  sigx = sub(ninth(sxx), mul(mux, mux));
+  sigxy = sub(ninth(sxy), mul(mux, muy));
   const f2 n1 = add(mul(mul(bc2(2.0f), mux), muy), bc2(BBD_C1));
   const f2 n2 = add(mul(bc2(2.0f), sigxy), bc2(BBD_C2));
   const f2 d1 = add(add(mul(mux, mux), mul(muy, muy)), bc2(BBD_C1));

@@ -29,6 +29,9 @@ namespace bbd {
 #ifndef BBD_WARPS
 #define BBD_WARPS 6
 #endif
+#ifndef BBD_SCATTER_REDUCE
+#define BBD_SCATTER_REDUCE 1
+#endif
 using SCfg = StripCfg<BBD_TILE_H, BBD_WARPS>;
 
 static thread_local char g_err[256] = "";
@@ -79,17 +82,43 @@ __global__ void __launch_bounds__(SCfg::NT) ident_kernel(const bbd_ident_args a)
 // warp partials are added by one thread per component.  No atomics.  red: [NW][12] floats.
 template <int K>
 __device__ __forceinline__ void block_reduce(float* red, int tid, const float* v, float* out) {
-  float r[K];
+#if BBD_SCATTER_REDUCE
+  if (K == 12) {
+    // Reduce-scatter over the warp: at every step a lane hands one half of its values to its partner
+    // and adds the partner's other half, so 16 shuffles (instead of 60) leave component (lane >> 1)
+    // summed over the warp in r[0].  Fixed order: deterministic.
+    const int lane = tid & 31;
+    float r[16];
 #pragma unroll
-  for (int i = 0; i < K; ++i) r[i] = v[i];
+    for (int i = 0; i < 16; ++i) r[i] = i < K ? v[i] : 0.0f;
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
+    for (int n = 8, off = 16; n >= 1; n >>= 1, off >>= 1) {
+      const bool upper = (lane & off) != 0;
 #pragma unroll
-    for (int i = 0; i < K; ++i) r[i] += __shfl_xor_sync(0xffffffffu, r[i], off);
-  }
-  if ((tid & 31) == 0) {
+      for (int i = 0; i < n; ++i) {
+        const float send = upper ? r[i] : r[i + n];
+        const float keep = upper ? r[i + n] : r[i];
+        r[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
+    const int comp = lane >> 1;
+    if ((lane & 1) == 0 && comp < K) red[(tid >> 5) * 12 + comp] = r[0];
+  } else
+#endif
+  {
+    float r[K];
 #pragma unroll
-    for (int i = 0; i < K; ++i) red[(tid >> 5) * 12 + i] = r[i];
+    for (int i = 0; i < K; ++i) r[i] = v[i];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+      for (int i = 0; i < K; ++i) r[i] += __shfl_xor_sync(0xffffffffu, r[i], off);
+    }
+    if ((tid & 31) == 0) {
+#pragma unroll
+      for (int i = 0; i < K; ++i) red[(tid >> 5) * 12 + i] = r[i];
+    }
   }
   __syncthreads();
   if (tid < K) {

@@ -46,7 +46,7 @@ struct StripSmem {
   float* tgt;    // [3][R2N]
   float* pred;   // [npred][3][R2N]  warped tiles: one per candidate (KEEP) or a single reused buffer
   float* tst;    // [6][R1N]  target window mean / variance term per channel
-  float* stash;  // [9][R1N]  window sums of the best candidate -> gradient coefficients
+  float* stash;  // [9][R1N]  window moments of the best candidate -> gradient coefficients
   float* best;   // [R1N]
   int* bidx;     // [R1N]
   float* gd;     // [INN]
@@ -260,7 +260,9 @@ BBD_HD void rs_stats(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx&
         w9pp_2(x + o0, x + o1, y + o0, y + o1, wsxx[c], wsxy[c], wsx[c]);
         const f2 muy = mk2(sm.tst[(2 * c) * C::R1N + j0], sm.tst[(2 * c) * C::R1N + j1]);
         const f2 sigy = mk2(sm.tst[(2 * c + 1) * C::R1N + j0], sm.tst[(2 * c + 1) * C::R1N + j1]);
-        const f2 v = ssim_channel2(wsx[c], wsxx[c], wsxy[c], muy, sigy);
+        f2 m0, m1, m2;  // the sums are dead from here on: keep the moments in their place
+        const f2 v = ssim_channel2(wsx[c], wsxx[c], wsxy[c], muy, sigy, m0, m1, m2);
+        wsx[c] = m0; wsxx[c] = m1; wsxy[c] = m2;
         ssim_sum = (c == 0) ? v : add(ssim_sum, v);
       }
       // 0.85 * mean_c(ssim) + 0.15 * mean_c(l1), packed (same order as photometric_mix)
@@ -314,6 +316,7 @@ BBD_HD void rs_stats(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx&
         wy.sig = sm.tst[(2 * c + 1) * C::R1N + j];
         SsimParts q;
         const float v = ssim_channel(wx[c], wy, q);
+        wx[c].sx = q.mux; wx[c].sxx = q.sigx; wx[c].sxy = q.sigxy;  // stash the moments, not the sums
         ssim_sum = (c == 0) ? v : add(ssim_sum, v);
       }
     }
@@ -364,15 +367,12 @@ BBD_HD float rs_select(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCt
         sm.anywin[win] = 1;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          WinX wx;
-          wx.sx = sm.stash[(3 * c) * C::R1N + j];
-          wx.sxx = sm.stash[(3 * c + 1) * C::R1N + j];
-          wx.sxy = sm.stash[(3 * c + 2) * C::R1N + j];
           WinY wy;
           wy.mu = sm.tst[(2 * c) * C::R1N + j];
           wy.sig = sm.tst[(2 * c + 1) * C::R1N + j];
-          SsimParts q;
-          ssim_channel(wx, wy, q);
+          SsimParts q;  // the stash holds the window moments of the winner (rs_stats)
+          ssim_from_moments(sm.stash[(3 * c) * C::R1N + j], sm.stash[(3 * c + 1) * C::R1N + j],
+                            sm.stash[(3 * c + 2) * C::R1N + j], wy, q);
           float ca, cb, cc;
           ssim_coefs(q, wy, g_ssim, ca, cb, cc);
           sm.stash[(3 * c) * C::R1N + j] = ca;
@@ -396,6 +396,15 @@ BBD_HD float rs_select(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCt
 // lanes.  The exchange buffer is warp-private ([10][32] floats per warp, carved out of the target
 // statistics planes, which are dead once the winners are selected), so the two passes are
 // separated by a warp barrier only.
+// does any active lane of the warp satisfy p?  (the CPU harness steps one thread at a time: p itself)
+BBD_HD bool warp_any(bool p) {
+#if defined(__CUDA_ARCH__)
+  return __any_sync(__activemask(), p) != 0;
+#else
+  return p;
+#endif
+}
+
 template <class C>
 BBD_HD float* rs_xch(StripSmem<C>& sm, const StripCtx& t, int buf) { return sm.tst + (t.warp * BBD_BWD_ROWS + buf) * 320; }
 
@@ -413,9 +422,12 @@ BBD_HD void rs_bwd_vertical(const bbd_reproj_args& a, StripSmem<C>& sm, const St
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy) {
     const int j = (q + dy) * C::P + t.lane;  // R1 row q+dy = window centre row q+1 + (dy-1)
-    if (sm.bidx[j] != k) continue;
-    any = true;
-    const float my = dy == 0 ? my0 : (dy == 2 ? my2 : 1.0f);
+    const bool mine = sm.bidx[j] == k;
+    // skip the row only if no lane of the warp has a winner there (uniform branch); otherwise every
+    // lane adds its coefficients times a 0/1 mask -- no divergence
+    if (!warp_any(mine)) continue;
+    any = any || mine;
+    const float my = mine ? (dy == 0 ? my0 : (dy == 2 ? my2 : 1.0f)) : 0.0f;
 #pragma unroll
     for (int e = 0; e < 9; ++e) v[e] += my * sm.stash[e * C::R1N + j];
   }
