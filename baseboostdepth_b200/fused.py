@@ -24,6 +24,10 @@ from . import _lib
 from .plan import LossPlan
 
 
+import os as _os
+
+# BBD_SIDE_STREAMS=0 keeps every kernel on the launch stream (debugging / A-B measurements)
+_USE_SIDE = _os.environ.get("BBD_SIDE_STREAMS", "1") != "0"
 _SIDE: Dict = {}
 
 
@@ -116,7 +120,7 @@ def start_side_branch(be, disps, pyramid, bhw, min_depth, max_depth, sql, need_g
     keep.append(scratch)
 
     join = None
-    if be.cuda:
+    if be.cuda and _USE_SIDE:
         main, (side_a, side_b) = torch.cuda.current_stream(), _side_streams(dev)
         fork = torch.cuda.Event()
         fork.record(main)
@@ -251,7 +255,7 @@ class _FusedLoss(torch.autograd.Function):
         d2d.scratch = scratch.data_ptr()
         S = len(gdisps)
         full_res_first = S > 1 and tuple(disps_c[0].shape[-2:]) == tuple(depth.shape[-2:])
-        if be.cuda and full_res_first:
+        if be.cuda and full_res_first and _USE_SIDE:
             # pass 2 of a full-resolution level does not read the row sums of pass 1: it runs on a helper
             # stream next to pass 1, the remaining levels follow pass 1 on this stream
             main, (side, _) = torch.cuda.current_stream(), _side_streams(gdepth.device)
