@@ -9,10 +9,10 @@ h = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
 H = rows[h]; ki, vi = H.index('Kernel Name'), H.index('Metric Value')
 seq = [(r[ki], float(r[vi].replace(',', ''))) for r in rows[h + 1:] if len(r) > vi]
 ends = [i for i, s in enumerate(seq) if 'd2d_backward_kernel' in s[0]]
-starts = [i for i, s in enumerate(seq) if 'pose_pack_kernel' in s[0]]
+starts = [i for i, s in enumerate(seq) if 'd2d_forward_kernel' in s[0]]
 a = max(i for i in starts if i < ends[-1]); b = ends[-1]
 tot = 0
-for n, v in seq[a - 1:b + 1]:
+for n, v in seq[a:b + 1]:
     us = v / 1000 if v > 500 else v
     tot += us
     print("%9.1f us  %s" % (us, n[:90]))
