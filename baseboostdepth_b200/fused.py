@@ -3,8 +3,8 @@
 ``fused_losses`` evaluates, for all scales of a step, what the reference spreads
 over ``generate_images_pred`` (``trainer.py:444-475``) and ``compute_losses``
 (``trainer.py:488-570``): disparity -> depth, identity pre-pass, warp + SSIM/L1 +
-per-pixel minimum, smoothness -- forward *and* backward -- in seven kernel
-launches, and returns the per-scale reprojection means and smoothness terms as
+per-pixel minimum, smoothness -- forward *and* backward -- in a dozen kernel
+launches (the small ones on helper streams next to the identity pre-pass), and returns the per-scale reprojection means and smoothness terms as
 differentiable tensors.  Gradients flow to the disparities and to the packed
 projection matrices ``P = (K @ T)[:, :3, :]``.
 

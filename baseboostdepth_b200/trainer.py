@@ -7,8 +7,8 @@ result keys of the reference (``trainer.py:444-475`` and ``:488-570``), so
     class FusedTrainer(FusedLossMixin, trainer.Trainer): pass
 
 trains with the reference's ``process_batch`` / ``run_epoch`` untouched.  The work
-itself is ``loss_step`` below: a plan lookup, a tiny batched ``K @ T`` and the
-seven kernel launches of ``fused.fused_losses``.
+itself is ``loss_step`` below: a plan lookup, a tiny batched ``K @ T``, the kernel
+launches of ``fused.fused_losses`` (nine forward, five backward) and the loss assembly.
 
 Differences a caller can observe (all deliberate):
   * ``outputs[("depth", 0, s)]`` is filled by ``compute_losses`` (not earlier) and

@@ -452,7 +452,7 @@ def run_ours(args):
             pass
         # headline: the step as the public API runs it in a training loop -- captured once, replayed as a
         # CUDA graph (graphed.GraphedLossStep does the same per staging slot); the eagerly launched step
-        # (Python + 11 launches + ~10 tensor ops per step) is reported beside it
+        # (Python + 14 launches + 3 tensor ops per step) is reported beside it
         eager_ms = step_ms
         if graph_ms is not None and graph_ms_max > 0:
             step_ms = graph_ms_max
