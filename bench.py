@@ -161,6 +161,7 @@ def cpu_reference_run(cfg, steps, warmup, sample_batch=None):
     sec = sum(times) / len(times)
     sample = (f"{c['batch']} of {cfg['batch']} samples of the workload, all scales and sources, "
               f"{steps} timed steps after {warmup} warm-up")
+    cpu_reference_run.last_probe = {str(k): v for k, v in probe.items()}   # forward-only seconds per thread count
     return pairs / sec, sec, sample, threads
 
 
@@ -474,7 +475,8 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": abytes["reproj"],
                          "step_algorithmic_bytes": abytes["total"],
                          "step_frac": abytes["total"] / (step_ms * 1e-3) / 1e9 / peak,
-                         "kernel_share_of_eager_step": kern_ms / eager_ms},
+                         "kernel_share_of_eager_step": kern_ms / eager_ms,
+                         "frac_vs_spec_sheet_8000_GBs": (achieved / 8000.0) if achieved else None},
             "clocks": clocks, "gpu_launches": launches,
         }
         if e2e_ms is not None:
@@ -494,7 +496,8 @@ def run_ours(args):
         if not args.no_cpu_baseline and world == 1:
             v, sec, sample, threads = cpu_reference_run(cfg, steps=2, warmup=1, sample_batch=4)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                                    "s_per_step": sec}
+                                    "s_per_step": sec,
+                                    "thread_probe_forward_s": getattr(cpu_reference_run, "last_probe", None)}
             # context only: the same oracle code run eagerly on this GPU (what the reference's ATen path costs)
             try:
                 line["cpu_baseline"]["same_code_eager_cuda_ms_per_step"] = eager_cuda_ms(cfg, dev)
