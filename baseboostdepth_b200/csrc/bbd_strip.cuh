@@ -23,6 +23,9 @@
 #ifndef BBD_PACKED_STATS
 #define BBD_PACKED_STATS 1
 #endif
+#ifndef BBD_PACKED_CHANNELS
+#define BBD_PACKED_CHANNELS 1
+#endif
 #ifndef BBD_BWD_ROWS
 #define BBD_BWD_ROWS 2  // rows a warp walks together in the backward (one exchange buffer each)
 #endif
@@ -301,6 +304,41 @@ BBD_HD void rs_stats(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx&
     const int j = i * C::P + t.lane;
     float ssim_sum = 0.0f, l1_sum = 0.0f;
     WinX wx[3];
+#if BBD_PACKED_STATS && BBD_PACKED_CHANNELS
+    // a single row: channels 0 and 1 of the same pixel as one packed pair (identical rounding and
+    // summation order), channel 2 scalar
+    if (!a.no_ssim) {
+      const float* x0 = pred;
+      const float* x1 = pred + C::R2N;
+      const float* y0 = sm.tgt;
+      const float* y1 = sm.tgt + C::R2N;
+      const f2 d = sub(ld2(y0, y1, ctr), ld2(x0, x1, ctr));
+      l1_sum = add(fabsf(d.x), fabsf(d.y));
+      f2 sx, sxx, sxy, m0, m1, m2;
+      w9pp_2(x0 + o, x1 + o, y0 + o, y1 + o, sxx, sxy, sx);
+      const f2 muy = mk2(sm.tst[j], sm.tst[2 * C::R1N + j]);
+      const f2 sigy = mk2(sm.tst[C::R1N + j], sm.tst[3 * C::R1N + j]);
+      const f2 v = ssim_channel2(sx, sxx, sxy, muy, sigy, m0, m1, m2);
+      ssim_sum = add(v.x, v.y);
+      wx[0].sx = m0.x; wx[0].sxx = m1.x; wx[0].sxy = m2.x;
+      wx[1].sx = m0.y; wx[1].sxx = m1.y; wx[1].sxy = m2.y;
+      {
+        const float* x = pred + 2 * C::R2N;
+        const float* y = sm.tgt + 2 * C::R2N;
+        l1_sum = add(l1_sum, fabsf(sub(y[ctr], x[ctr])));
+        wx[2].sx = w9(x + o);
+        wx[2].sxx = w9p(x + o, x + o);
+        wx[2].sxy = w9p(x + o, y + o);
+        WinY wy;
+        wy.mu = sm.tst[4 * C::R1N + j];
+        wy.sig = sm.tst[5 * C::R1N + j];
+        SsimParts q;
+        const float v2 = ssim_channel(wx[2], wy, q);
+        wx[2].sx = q.mux; wx[2].sxx = q.sigx; wx[2].sxy = q.sigxy;
+        ssim_sum = add(ssim_sum, v2);
+      }
+    } else
+#endif
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float* x = pred + c * C::R2N;
