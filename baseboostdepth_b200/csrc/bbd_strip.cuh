@@ -156,6 +156,22 @@ BBD_HD void rs_load_wait() {
 // overlaps it with the first candidate's warp phase (which does not read the target) and calls
 // rs_load_wait() before the barrier that precedes the first use of sm.tgt.  (Staging the depth
 // tile the same way was measured: no gain, its loads are already hidden.)
+// window sum and sum of squares of one plane at two positions (same order as w9 / w9p)
+BBD_HD void w9sq_2(const float* p0, const float* p1, f2& s, f2& ss) {
+  const int offs[9] = {0, 1, 2, 32, 33, 34, 64, 65, 66};
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const f2 y = ld2(p0, p1, offs[i]);
+    if (i == 0) { s = y; ss = mul(y, y); }
+    else { s = add(s, y); ss = add(ss, mul(y, y)); }
+  }
+}
+// target_stats for two positions
+BBD_HD void target_stats2(const f2& sy, const f2& syy, f2& mu, f2& sig) {
+  mu = ninth(sy);
+  sig = sub(ninth(syy), mul(mu, mu));
+}
+
 template <class C>
 BBD_HD void rs_load_target(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t, int tid) {
   const int H = a.height, W = a.width, HW = H * W;
@@ -188,6 +204,7 @@ BBD_HD bool rs_center(const bbd_reproj_args& a, const StripCtx& t, int i, int& p
 template <class C>
 BBD_HD void rs_target_stats(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& t) {
   if (a.no_ssim) return;
+  // (packing these rows like rs_stats was measured: spills at 96 registers, kernel +10 us)
   for (int i = t.warp; i < C::R1H; i += C::NW) {
     int py;
     if (!rs_center<C>(a, t, i, py)) continue;
@@ -572,7 +589,30 @@ template <class C>
 BBD_HD void is_target_stats(const bbd_ident_args& a, IdentStripSmem<C>& sm, const StripCtx& t) {
   if (a.no_ssim) return;
   const int H = a.height, W = a.width;
-  for (int q = t.warp; q < C::TH; q += C::NW) {
+  int q_begin = t.warp;
+#if BBD_PACKED_STATS
+  {
+    const int q0 = t.warp, q1 = t.warp + C::NW;
+    q_begin = t.warp + 2 * C::NW;
+    int py0, py1;
+    const bool v0 = is_owned<C>(t, q0, H, W, py0), v1 = is_owned<C>(t, q1, H, W, py1);
+    if (v0 || v1) {
+      const int lane = (t.lane < 1) ? 1 : t.lane;
+      const int o0 = (q0 + 1) * C::P + lane - 1, o1 = (q1 + 1) * C::P + lane - 1;
+      const int j0 = q0 * C::P + t.lane, j1 = q1 * C::P + t.lane;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* y = sm.tgt + c * C::R2N;
+        f2 sy, syy, mu, sig;
+        w9sq_2(y + o0, y + o1, sy, syy);
+        target_stats2(sy, syy, mu, sig);
+        if (v0) { sm.tst[(2 * c) * C::INN + j0] = mu.x; sm.tst[(2 * c + 1) * C::INN + j0] = sig.x; }
+        if (v1) { sm.tst[(2 * c) * C::INN + j1] = mu.y; sm.tst[(2 * c + 1) * C::INN + j1] = sig.y; }
+      }
+    }
+  }
+#endif
+  for (int q = q_begin; q < C::TH; q += C::NW) {
     int py;
     if (!is_owned<C>(t, q, H, W, py)) continue;
     const int o = (q + 1) * C::P + t.lane - 1;  // window top-left in R2 coordinates
@@ -590,7 +630,47 @@ BBD_HD void is_target_stats(const bbd_ident_args& a, IdentStripSmem<C>& sm, cons
 template <class C>
 BBD_HD void is_candidate(const bbd_ident_args& a, IdentStripSmem<C>& sm, const StripCtx& t, int jcand, const float* noise) {
   const int H = a.height, W = a.width;
-  for (int q = t.warp; q < C::TH; q += C::NW) {
+  int q_begin = t.warp;
+#if BBD_PACKED_STATS
+  // rows q0 = warp and q1 = warp + NW as one packed pair (same operation order as the scalar path)
+  if (!a.no_ssim) {
+    static_assert(C::TH >= 2 * C::NW, "packed identity statistics need two full row sets");
+    const int q0 = t.warp, q1 = t.warp + C::NW;
+    q_begin = t.warp + 2 * C::NW;
+    int py0, py1;
+    const bool v0 = is_owned<C>(t, q0, H, W, py0), v1 = is_owned<C>(t, q1, H, W, py1);
+    if (v0 || v1) {
+      const int lane = (t.lane < 1) ? 1 : t.lane;  // keep the window inside the plane for idle lanes
+      const int o0 = (q0 + 1) * C::P + lane - 1, o1 = (q1 + 1) * C::P + lane - 1;
+      const int j0 = q0 * C::P + t.lane, j1 = q1 * C::P + t.lane;
+      f2 ssim_sum = bc2(0.0f), l1_sum = bc2(0.0f);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* x = sm.src + c * C::R2N;
+        const float* y = sm.tgt + c * C::R2N;
+        const f2 d = sub(ld2(y + o0, y + o1, C::P + 1), ld2(x + o0, x + o1, C::P + 1));
+        const f2 l1 = mk2(fabsf(d.x), fabsf(d.y));
+        l1_sum = (c == 0) ? l1 : add(l1_sum, l1);
+        f2 sx, sxx, sxy, m0, m1, m2;
+        w9pp_2(x + o0, x + o1, y + o0, y + o1, sxx, sxy, sx);
+        const f2 muy = mk2(sm.tst[(2 * c) * C::INN + j0], sm.tst[(2 * c) * C::INN + j1]);
+        const f2 sigy = mk2(sm.tst[(2 * c + 1) * C::INN + j0], sm.tst[(2 * c + 1) * C::INN + j1]);
+        const f2 v = ssim_channel2(sx, sxx, sxy, muy, sigy, m0, m1, m2);
+        ssim_sum = (c == 0) ? v : add(ssim_sum, v);
+      }
+      const f2 loss = add(mul(bc2(BBD_W_SSIM), mul(ssim_sum, bc2(BBD_THIRD))), mul(bc2(BBD_W_L1), mul(l1_sum, bc2(BBD_THIRD))));
+      if (v0) {
+        const float val = add(loss.x, mul(noise[py0 * W + t.u], a.noise_scale));
+        if (jcand == 0 || val < sm.best[j0]) { sm.best[j0] = val; sm.arg[j0] = jcand; }
+      }
+      if (v1) {
+        const float val = add(loss.y, mul(noise[py1 * W + t.u], a.noise_scale));
+        if (jcand == 0 || val < sm.best[j1]) { sm.best[j1] = val; sm.arg[j1] = jcand; }
+      }
+    }
+  }
+#endif
+  for (int q = q_begin; q < C::TH; q += C::NW) {
     int py;
     if (!is_owned<C>(t, q, H, W, py)) continue;
     const int o = (q + 1) * C::P + t.lane - 1, ctr = o + C::P + 1;
