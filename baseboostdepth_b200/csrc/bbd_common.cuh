@@ -159,6 +159,40 @@ BBD_HD void project_pixel(const Cam& c, int px, int py, float depth, int W, int 
   s.y0 = (int)floorf(iy);
 }
 
+// project_pixel for two pixels of one column (rows py0, py1) at once: the rounded multiply / add / fma
+// chain runs on packed fp32x2 values (identical rounding per value), the two perspective divisions,
+// the clip and the floor stay scalar.
+BBD_HD void project_finish(const Cam& c, float ix, float iy, Sample& s) {
+  const float wmax = c.wm1, hmax = c.hm1;
+  if (!(ix > 0.0f)) { ix = 0.0f; s.mx = 0.0f; } else if (ix >= wmax) { ix = wmax; s.mx = 0.0f; } else { s.mx = 1.0f; }
+  if (!(iy > 0.0f)) { iy = 0.0f; s.my = 0.0f; } else if (iy >= hmax) { iy = hmax; s.my = 0.0f; } else { s.my = 1.0f; }
+  s.ix = ix;
+  s.iy = iy;
+  s.x0 = (int)floorf(ix);
+  s.y0 = (int)floorf(iy);
+}
+BBD_HD void project_pixel2(const Cam& c, int px, int py0, int py1, float depth0, float depth1, Sample& s0, Sample& s1) {
+  const float x = (float)px;
+  const f2 y = mk2((float)py0, (float)py1), one = bc2(1.0f), d = mk2(depth0, depth1);
+  const f2 rx = fma_(bc2(c.ik[2]), one, fma_(bc2(c.ik[1]), y, bc2(mul(c.ik[0], x))));
+  const f2 ry = fma_(bc2(c.ik[5]), one, fma_(bc2(c.ik[4]), y, bc2(mul(c.ik[3], x))));
+  const f2 rz = fma_(bc2(c.ik[8]), one, fma_(bc2(c.ik[7]), y, bc2(mul(c.ik[6], x))));
+  const f2 X = mul(d, rx), Y = mul(d, ry), Z = mul(d, rz);
+  const f2 cx = fma_(bc2(c.p[3]), one, fma_(bc2(c.p[2]), Z, fma_(bc2(c.p[1]), Y, mul(bc2(c.p[0]), X))));
+  const f2 cy = fma_(bc2(c.p[7]), one, fma_(bc2(c.p[6]), Z, fma_(bc2(c.p[5]), Y, mul(bc2(c.p[4]), X))));
+  const f2 cz = fma_(bc2(c.p[11]), one, fma_(bc2(c.p[10]), Z, fma_(bc2(c.p[9]), Y, mul(bc2(c.p[8]), X))));
+  const f2 zz = add(cz, bc2(1e-7f));
+  const f2 ux = div_(cx, zz), uy = div_(cy, zz);
+  const f2 gx = mul(sub(div_const(ux, c.wm1, c.rw), bc2(0.5f)), bc2(2.0f));
+  const f2 gy = mul(sub(div_const(uy, c.hm1, c.rh), bc2(0.5f)), bc2(2.0f));
+  const f2 ix = mul(mul(add(gx, one), bc2(0.5f)), bc2(c.wm1));
+  const f2 iy = mul(mul(add(gy, one), bc2(0.5f)), bc2(c.hm1));
+  s0.rx = rx.x; s0.ry = ry.x; s0.rz = rz.x; s0.X = X.x; s0.Y = Y.x; s0.Z = Z.x; s0.zz = zz.x; s0.ux = ux.x; s0.uy = uy.x;
+  s1.rx = rx.y; s1.ry = ry.y; s1.rz = rz.y; s1.X = X.y; s1.Y = Y.y; s1.Z = Z.y; s1.zz = zz.y; s1.ux = ux.y; s1.uy = uy.y;
+  project_finish(c, ix.x, iy.x, s0);
+  project_finish(c, ix.y, iy.y, s1);
+}
+
 // Bilinear taps of one channel plane (ATen grid_sampler_2d, bilinear): weights from the
 // opposite corners, out-of-range taps contribute nothing, accumulation is an FMA chain.
 struct Taps {

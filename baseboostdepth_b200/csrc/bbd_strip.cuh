@@ -23,6 +23,9 @@
 #ifndef BBD_PACKED_STATS
 #define BBD_PACKED_STATS 1
 #endif
+#ifndef BBD_PACKED_PROJECT
+#define BBD_PACKED_PROJECT 1
+#endif
 #ifndef BBD_PACKED_CHANNELS
 #define BBD_PACKED_CHANNELS 1
 #endif
@@ -235,6 +238,30 @@ BBD_HD void rs_warp(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& 
   const float* depth = a.depth + ((size_t)t.s * a.batch + t.b) * HW;
   float* pred = sm.pred + (KEEP ? (size_t)k * 3 * C::R2N : 0);
   constexpr int ITERS = (C::R2H + C::NW - 1) / C::NW;
+#if BBD_PACKED_PROJECT
+  // rows in pairs: the projection arithmetic of two rows of the column runs packed
+  BBD_UNROLL(BBD_UNROLL_WARP / 2)
+  for (int m = 0; m < ITERS; m += 2) {
+    const int j0 = t.warp + m * C::NW;
+    if (C::R2H % C::NW != 0 && j0 >= C::R2H) break;
+    const int j1raw = j0 + C::NW;
+    const bool two = (m + 1 < ITERS) && j1raw < C::R2H;
+    const int j1 = two ? j1raw : j0;
+    const int py0 = reflect1(t.y0 - 2 + j0, H), py1 = reflect1(t.y0 - 2 + j1, H);
+    Sample s[2];
+    project_pixel2(cam, t.px, py0, py1, depth[py0 * W + t.px], depth[py1 * W + t.px], s[0], s[1]);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (r == 1 && !two) break;
+      Taps tp;
+      make_taps(s[r], W, H, tp);
+      const int i = (r ? j1 : j0) * C::P + t.lane;
+      pred[i] = tap_channel(src, tp);
+      pred[C::R2N + i] = tap_channel(src + HW, tp);
+      pred[2 * C::R2N + i] = tap_channel(src + 2 * HW, tp);
+    }
+  }
+#else
   BBD_UNROLL(BBD_UNROLL_WARP)
   for (int m = 0; m < ITERS; ++m) {
     const int j = t.warp + m * C::NW;
@@ -249,6 +276,7 @@ BBD_HD void rs_warp(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx& 
     pred[C::R2N + i] = tap_channel(src + HW, tp);
     pred[2 * C::R2N + i] = tap_channel(src + 2 * HW, tp);
   }
+#endif
 }
 
 template <class C, bool KEEP>
