@@ -307,18 +307,28 @@ BBD_HD float ssim_from_moments(float mux, float sigx, float sigxy, const WinY& w
 // Two window centres at once (same operation order, hence bit-identical to ssim_channel).
 BBD_HD f2 ninth(const f2& s) { return div_const(s, 9.0f, 0.111111111938953399658203125f); }
 // (also hands back the window moments, which is what the winner selection keeps for the backward)
+struct SsimParts2 {
+  f2 mux, sigx, sigxy, n1, n2, d1, d2, r, raw;
+};
+BBD_HD f2 ssim_from_moments2(const f2& mux, const f2& sigx, const f2& sigxy, const f2& muy, const f2& sigy, SsimParts2& q) {
+  q.mux = mux;
+  q.sigx = sigx;
+  q.sigxy = sigxy;
+  q.n1 = add(mul(mul(bc2(2.0f), mux), muy), bc2(BBD_C1));
+  q.n2 = add(mul(bc2(2.0f), sigxy), bc2(BBD_C2));
+  q.d1 = add(add(mul(mux, mux), mul(muy, muy)), bc2(BBD_C1));
+  q.d2 = add(add(sigx, sigy), bc2(BBD_C2));
+  q.r = div_(mul(q.n1, q.n2), mul(q.d1, q.d2));
+  q.raw = mul(sub(bc2(1.0f), q.r), bc2(0.5f));
+  return mk2(fminf(fmaxf(q.raw.x, 0.0f), 1.0f), fminf(fmaxf(q.raw.y, 0.0f), 1.0f));
+}
 BBD_HD f2 ssim_channel2(const f2& sx, const f2& sxx, const f2& sxy, const f2& muy, const f2& sigy, f2& mux, f2& sigx,
                         f2& sigxy) {
   mux = ninth(sx);
   sigx = sub(ninth(sxx), mul(mux, mux));
   sigxy = sub(ninth(sxy), mul(mux, muy));
-  const f2 n1 = add(mul(mul(bc2(2.0f), mux), muy), bc2(BBD_C1));
-  const f2 n2 = add(mul(bc2(2.0f), sigxy), bc2(BBD_C2));
-  const f2 d1 = add(add(mul(mux, mux), mul(muy, muy)), bc2(BBD_C1));
-  const f2 d2 = add(add(sigx, sigy), bc2(BBD_C2));
-  const f2 r = div_(mul(n1, n2), mul(d1, d2));
-  const f2 raw = mul(sub(bc2(1.0f), r), bc2(0.5f));
-  return mk2(fminf(fmaxf(raw.x, 0.0f), 1.0f), fminf(fmaxf(raw.y, 0.0f), 1.0f));
+  SsimParts2 q;
+  return ssim_from_moments2(mux, sigx, sigxy, muy, sigy, q);
 }
 
 // Coefficients (a, b, c) such that d(value)/d x(u) = a + b*x(u) + c*y(u) for every pixel u of
@@ -338,6 +348,26 @@ BBD_HD void ssim_coefs(const SsimParts& q, const WinY& wy, float g, float& a, fl
   a = k * r_mux;
   b = k * 2.0f * r_sigx;
   c = k * r_sigxy;
+}
+
+// ssim_coefs for two channels at once (gradient-only arithmetic, packed)
+BBD_HD void ssim_coefs2(const SsimParts2& q, const f2& muy, float g, f2& a, f2& b, f2& c) {
+  const f2 gr = bc2(-0.5f * g);
+  const f2 den = mul(q.d1, q.d2);
+  const f2 invd = mk2(rcp_approx(den.x), rcp_approx(den.y));
+  const f2 two = bc2(2.0f);
+  const f2 r_d = mul(sub(bc2(0.0f), q.r), invd);
+  const f2 r_sigxy = mul(mul(invd, q.n1), two);
+  const f2 r_sigx = mul(r_d, q.d1);
+  // direct terms, then the paths through sigma_x and sigma_xy
+  f2 r_mux = fma_(mul(mul(invd, q.n2), two), muy, mul(mul(mul(r_d, q.d2), two), q.mux));
+  r_mux = sub(r_mux, fma_(mul(two, q.mux), r_sigx, mul(muy, r_sigxy)));
+  const f2 k = mul(gr, bc2(1.0f / 9.0f));
+  a = mul(k, r_mux);
+  b = mul(mul(k, two), r_sigx);
+  c = mul(k, r_sigxy);
+  if (!(q.raw.x >= 0.0f && q.raw.x <= 1.0f)) { a.x = b.x = c.x = 0.0f; }
+  if (!(q.raw.y >= 0.0f && q.raw.y <= 1.0f)) { a.y = b.y = c.y = 0.0f; }
 }
 
 // Same for the target image: d(value)/d y(u) = a + b*y(u) + c*x(u)   (used by the SSIM operator).

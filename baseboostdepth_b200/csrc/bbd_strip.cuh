@@ -448,8 +448,26 @@ BBD_HD float rs_select(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCt
     if (a.need_grad) {
       if (win >= 0 && !a.no_ssim) {
         sm.anywin[win] = 1;
+#if BBD_PACKED_STATS && BBD_PACKED_CHANNELS
+        {  // channels 0 and 1 as one packed pair (the exact part keeps its rounding), channel 2 below
+          const f2 mux = mk2(sm.stash[j], sm.stash[3 * C::R1N + j]);
+          const f2 sigx = mk2(sm.stash[C::R1N + j], sm.stash[4 * C::R1N + j]);
+          const f2 sigxy = mk2(sm.stash[2 * C::R1N + j], sm.stash[5 * C::R1N + j]);
+          const f2 muy = mk2(sm.tst[j], sm.tst[2 * C::R1N + j]);
+          const f2 sigy = mk2(sm.tst[C::R1N + j], sm.tst[3 * C::R1N + j]);
+          SsimParts2 q2;
+          ssim_from_moments2(mux, sigx, sigxy, muy, sigy, q2);
+          f2 ca, cb, cc;
+          ssim_coefs2(q2, muy, g_ssim, ca, cb, cc);
+          sm.stash[j] = ca.x; sm.stash[C::R1N + j] = cb.x; sm.stash[2 * C::R1N + j] = cc.x;
+          sm.stash[3 * C::R1N + j] = ca.y; sm.stash[4 * C::R1N + j] = cb.y; sm.stash[5 * C::R1N + j] = cc.y;
+        }
+        constexpr int C_BEGIN = 2;
+#else
+        constexpr int C_BEGIN = 0;
+#endif
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+        for (int c = C_BEGIN; c < 3; ++c) {
           WinY wy;
           wy.mu = sm.tst[(2 * c) * C::R1N + j];
           wy.sig = sm.tst[(2 * c + 1) * C::R1N + j];
