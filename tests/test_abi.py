@@ -66,3 +66,54 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_argument_errors_are_codes_not_crashes(lib_path):
+    """Error behaviour of the boundary (include/bbd_loss.h): bad arguments give a negative BBD_E_* code and
+    a message in bbd_last_error_string(); nothing throws, exits or touches the device.  (Argument checks
+    run before any CUDA call, so this works in the GPU-less build container.)"""
+    dll = ctypes.CDLL(lib_path)
+    dll.bbd_last_error_string.restype = ctypes.c_char_p
+    E_ARG, E_RANGE = -1, -2
+    null = ctypes.c_void_p(None)
+
+    assert dll.bbd_reproj_fused(null, null) == E_ARG
+    assert b"reproj" in dll.bbd_last_error_string()
+    assert dll.bbd_ident_forward(null, null) == E_ARG
+    assert dll.bbd_smooth_fused(null, null) == E_ARG
+    assert dll.bbd_disp_to_depth_forward(null, null) == E_ARG
+    assert dll.bbd_disp_to_depth_backward(null, null) == E_ARG
+    assert dll.bbd_u8_to_f32(null, null, ctypes.c_size_t(16), null) == E_ARG
+    assert dll.bbd_u8_to_f32(null, null, ctypes.c_size_t(0), null) == E_ARG      # null wins over "nothing to do"
+
+    # a structurally complete argument block with a candidate count outside the supported range
+    ra = _lib.ReprojArgs()
+    buf = (ctypes.c_float * 4)()
+    tab = (ctypes.c_int32 * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p).value
+    for name in ("target", "depth", "inv_K", "P", "ident_min", "loss_part"):
+        setattr(ra, name, p)
+    ra.tab.hdr = ra.tab.rep = ra.tab.ident = ctypes.cast(tab, ctypes.c_void_p).value
+    ra.batch, ra.height, ra.width, ra.num_scales, ra.need_grad = 1, 32, 64, 1, 0
+    ra.max_rep = 0
+    assert dll.bbd_reproj_fused(ctypes.byref(ra), null) == E_RANGE
+    ra.max_rep = _lib.MAX_REP + 1
+    assert dll.bbd_reproj_fused(ctypes.byref(ra), null) == E_RANGE
+    ra.max_rep, ra.height = 2, 1
+    assert dll.bbd_reproj_fused(ctypes.byref(ra), null) == E_ARG                 # reflection padding needs >= 2 rows
+    ra.height, ra.need_grad = 32, 1
+    assert dll.bbd_reproj_fused(ctypes.byref(ra), null) == E_ARG                 # gradient buffers missing
+    assert b"gradient" in dll.bbd_last_error_string()
+
+    da = _lib.D2DArgs()
+    da.batch, da.levels, da.height, da.width = 1, _lib.MAX_SCALES + 1, 32, 64
+    da.depth = p
+    assert dll.bbd_disp_to_depth_forward(ctypes.byref(da), null) == E_RANGE
+    da.levels = 1
+    da.h[0], da.w[0], da.disp[0] = 12, 20, p       # 32/12 is not an integer factor
+    da.gdepth = da.gscale = p
+    da.gdisp[0] = p
+    assert dll.bbd_disp_to_depth_backward(ctypes.byref(da), null) == E_RANGE
+
+    assert dll.bbd_loss_combine_forward(0, null, null, null, ctypes.c_float(4.0), null, null, null) == E_ARG
+    assert dll.bbd_loss_combine_forward(9, p, p, p, ctypes.c_float(4.0), p, p, null) == E_RANGE
