@@ -23,6 +23,9 @@
 #ifndef BBD_PACKED_STATS
 #define BBD_PACKED_STATS 1
 #endif
+#ifndef BBD_PACKED_VERTICAL
+#define BBD_PACKED_VERTICAL 1
+#endif
 #ifndef BBD_PACKED_PROJECT
 #define BBD_PACKED_PROJECT 1
 #endif
@@ -516,10 +519,36 @@ BBD_HD void rs_bwd_vertical(const bbd_reproj_args& a, StripSmem<C>& sm, const St
   if (py >= a.height || t.lane < 1 || t.lane > 30) return;
   float* x = rs_xch<C>(sm, t, buf);
   const float my0 = (py == 1) ? 2.0f : 1.0f, my2 = (py == a.height - 2) ? 2.0f : 1.0f;
+  bool any = false;
+#if BBD_PACKED_STATS && BBD_PACKED_VERTICAL
+  // the nine coefficient planes as four packed pairs + one scalar
+  f2 v2[4];
+  float v8 = 0.0f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) v2[e] = bc2(0.0f);
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int j = (q + dy) * C::P + t.lane;
+    const bool mine = sm.bidx[j] == k;
+    if (!warp_any(mine)) continue;
+    any = any || mine;
+    const float my = mine ? (dy == 0 ? my0 : (dy == 2 ? my2 : 1.0f)) : 0.0f;
+    const f2 m2 = bc2(my);
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      v2[e] = fma_(m2, mk2(sm.stash[(2 * e) * C::R1N + j], sm.stash[(2 * e + 1) * C::R1N + j]), v2[e]);
+    v8 += my * sm.stash[8 * C::R1N + j];
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    x[(2 * e) * 32 + t.lane] = v2[e].x;
+    x[(2 * e + 1) * 32 + t.lane] = v2[e].y;
+  }
+  x[8 * 32 + t.lane] = v8;
+#else
   float v[9];
 #pragma unroll
   for (int e = 0; e < 9; ++e) v[e] = 0.0f;
-  bool any = false;
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy) {
     const int j = (q + dy) * C::P + t.lane;  // R1 row q+dy = window centre row q+1 + (dy-1)
@@ -534,6 +563,7 @@ BBD_HD void rs_bwd_vertical(const bbd_reproj_args& a, StripSmem<C>& sm, const St
   }
 #pragma unroll
   for (int e = 0; e < 9; ++e) x[e * 32 + t.lane] = v[e];
+#endif
   x[9 * 32 + t.lane] = any ? 1.0f : 0.0f;
 }
 
