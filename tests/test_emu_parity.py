@@ -139,3 +139,49 @@ def test_step_leaves_no_reference_cycle():
         assert all(r() is None for r in refs)
     finally:
         gc.enable()
+
+
+@pytest.mark.parametrize("name,baselines,trimin,decomp", [
+    ("all_stereo_plain", ["s", "s"], False, False),
+    ("all_stereo_trimin", ["s", "s", "s"], True, False),
+    ("single_sample_stereo", ["s"], False, False),
+    ("single_sample_b3_decomp", [3], True, True),
+    ("one_of_each_trimin", ["s", 1, 2, 3], True, False),
+])
+def test_degenerate_batch_layouts(name, baselines, trimin, decomp):
+    """Batch layouts at the edges of the candidate tables (no temporal source at all, a single sample, every
+    baseline once): kernel source stepped on the CPU vs the oracle, losses / gradients / selections."""
+    from baseboostdepth_b200.synthetic import make_batch, make_noise
+    from baseboostdepth_b200.trainer import plan_for
+    H, W, B = 32, 56, len(baselines)
+    cfg = dict(batch=B, height=H, width=W, baselines=baselines, trimin=trimin, decomp=decomp, scales=(0, 1), seed=31)
+    opt = O.default_opt(height=H, width=W, scales=[0, 1], trimin=trimin, decomp=decomp, pose_error=5.5, batch_size=B)
+
+    gi, go, gp = make_batch(device="cpu", pose_error=5.5, **cfg)
+    s_rows = gi[("color", "s", 0)].shape[0] if ("color", "s", 0) in gi else None
+    plan = plan_for(gi["ordering"], trimin, decomp, s_rows)
+    noise = make_noise(plan, H, W, seed=5)
+    ref, aux = O.run(gi, go, opt, noise, num_scales=4)
+    ref["loss"].backward()
+    ref_grads = {k: v.grad.clone() for k, v in gp.items() if v.grad is not None}
+
+    hi, ho, hp = make_batch(device="cpu", pose_error=5.5, **cfg)
+    losses, plan2 = run_fused(hi, ho, opt, noise, 4, backend=emu_backend(), groups=aux["groups"])
+    for k, v in ref.items():
+        assert abs(float(losses[k].detach()) - float(v.detach())) <= 2e-6 * max(1.0, abs(float(v.detach()))), (name, k)
+    losses["loss"].backward()
+    for k, gr in ref_grads.items():
+        assert hp[k].grad is not None, (name, k)
+        assert rel_l2(hp[k].grad, gr) <= 2e-5, (name, k, rel_l2(hp[k].grad, gr))
+    win = ho["argmin"]
+    order = [b for grp in aux["groups"] for b in plan2.group_members[grp]]
+    for i, s in enumerate([0, 1]):
+        args = torch.cat(aux["argmin"][s], 0)
+        mine = win[i][order].long()
+        agree = mine == args
+        if not bool(agree.all()):
+            margins = []
+            for p in aux["planes"][s]:
+                top = torch.topk(-p, 2, dim=1).values
+                margins.append(top[:, 0] - top[:, 1])
+            assert bool((agree | (torch.cat(margins, 0) <= 1e-6)).all()), (name, s)
