@@ -291,3 +291,43 @@ def test_disp_to_depth_against_autograd(sizes):
         parts = backward(True)
         for l in range(S):
             assert torch.equal(parts[l], whole[l]), l
+
+
+def test_operator_size_sweep():
+    """Tier-A operators over a sweep of small and awkward sizes (2-pixel images, single rows of tiles, widths
+    around the 28-column tile and the 32-lane pitch): SSIM, smoothness and grid_sample vs the ATen ops."""
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(99)
+    sizes = [(2, 2), (2, 7), (3, 28), (5, 29), (4, 31), (6, 32), (7, 33), (17, 57), (16, 56), (33, 5)]
+    for H, W in sizes:
+        x0, y0 = torch.rand(1, 3, H, W, generator=gen), torch.rand(1, 3, H, W, generator=gen)
+        w = torch.rand(1, 3, H, W, generator=gen)
+        got, ref = [], []
+        for mine, res in ((True, got), (False, ref)):
+            x = x0.clone().requires_grad_(True)
+            out = L.SSIM()(x, y0) if mine else O.ssim(x, y0)
+            (out * w).sum().backward()
+            res.extend([out.detach(), x.grad])
+        assert max_abs(got[0], ref[0]) <= 1e-6, ("ssim", H, W)
+        assert rel_l2(got[1], ref[1]) <= 5e-5, ("ssim grad", H, W, rel_l2(got[1], ref[1]))
+
+        d0 = 0.05 + torch.rand(1, 1, H, W, generator=gen)
+        got, ref = [], []
+        for mine, res in ((True, got), (False, ref)):
+            d = d0.clone().requires_grad_(True)
+            loss = (L.get_smooth_loss if mine else O.smooth_loss)(d, x0)
+            loss.backward()
+            res.extend([loss.detach(), d.grad])
+        assert abs(float(got[0]) - float(ref[0])) <= 1e-6, ("smooth", H, W)
+        assert rel_l2(got[1], ref[1]) <= 1e-5, ("smooth grad", H, W)
+
+        base = torch.rand(1, 2, H, W, generator=gen) * 2.4 - 1.2
+        got, ref = [], []
+        for fn, res in ((L.grid_sample, got),
+                        (lambda i, g: F.grid_sample(i, g, align_corners=True, padding_mode="border"), ref)):
+            raw = base.clone().requires_grad_(True)
+            out = fn(x0, raw.permute(0, 2, 3, 1))
+            (out * w).sum().backward()
+            res.extend([out.detach(), raw.grad])
+        assert max_abs(got[0], ref[0]) <= 1e-6, ("grid_sample", H, W)
+        assert max_abs(got[1], ref[1]) <= 2e-5, ("grid_sample grad", H, W)
