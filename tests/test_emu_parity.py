@@ -185,3 +185,27 @@ def test_degenerate_batch_layouts(name, baselines, trimin, decomp):
                 top = torch.topk(-p, 2, dim=1).values
                 margins.append(top[:, 0] - top[:, 1])
             assert bool((agree | (torch.cat(margins, 0) <= 1e-6)).all()), (name, s)
+
+
+@pytest.mark.parametrize("H,W", [(16, 32), (24, 56), (48, 64), (40, 120), (16, 200)])
+def test_fused_size_sweep(H, W):
+    """Frame sizes around the tile geometry (one tile, exact multiples of 28 / 16, wide and flat, ragged both
+    ways), tri-min with a mixed batch: kernel source stepped on the CPU vs the oracle."""
+    from baseboostdepth_b200.synthetic import make_batch, make_noise
+    from baseboostdepth_b200.trainer import plan_for
+    baselines = [2, "s", 1]
+    cfg = dict(batch=3, height=H, width=W, baselines=baselines, trimin=True, decomp=False, scales=(0, 1, 2, 3), seed=41)
+    opt = O.default_opt(height=H, width=W, scales=[0, 1, 2, 3], trimin=True, decomp=False, batch_size=3)
+    gi, go, gp = make_batch(device="cpu", **cfg)
+    plan = plan_for(gi["ordering"], True, False, gi[("color", "s", 0)].shape[0])
+    noise = make_noise(plan, H, W, seed=6)
+    ref, aux = O.run(gi, go, opt, noise, num_scales=4)
+    ref["loss"].backward()
+    hi, ho, hp = make_batch(device="cpu", **cfg)
+    losses, _ = run_fused(hi, ho, opt, noise, 4, backend=emu_backend(), groups=aux["groups"])
+    for k, v in ref.items():
+        assert abs(float(losses[k].detach()) - float(v.detach())) <= 2e-6 * max(1.0, abs(float(v.detach()))), k
+    losses["loss"].backward()
+    for k, v in gp.items():
+        if v.grad is not None:
+            assert rel_l2(hp[k].grad, v.grad) <= 2e-5, (k, rel_l2(hp[k].grad, v.grad))
