@@ -35,7 +35,8 @@ class ReprojArgs(C.Structure):
                 ("no_ssim", C.c_int32), ("need_grad", C.c_int32), ("max_rep", C.c_int32), ("num_pose", C.c_int32),
                 ("target", fp), ("frames", fp * MAX_FRAMES), ("depth", fp), ("inv_K", fp), ("P", fp),
                 ("ident_min", fp), ("tab", Tables), ("loss_part", fp), ("gpose_part", fp), ("gdepth", fp),
-                ("winner", fp), ("ident_arg", fp)]
+                ("winner", fp), ("ident_arg", fp), ("frames_rgba", fp * MAX_FRAMES), ("min_rep", C.c_int32),
+                ("force_tile", C.c_int32)]
 
 
 class SmoothArgs(C.Structure):
@@ -62,7 +63,7 @@ EXPORTS = [
     "bbd_backproject_backward", "bbd_project_forward", "bbd_project_chunks", "bbd_project_backward",
     "bbd_ssim_forward", "bbd_ssim_backward", "bbd_pose_pack_forward", "bbd_pose_pack_backward",
     "bbd_pose_forward", "bbd_pose_backward", "bbd_grid_sample_forward", "bbd_grid_sample_backward",
-    "bbd_u8_to_f32", "bbd_loss_combine_forward", "bbd_loss_combine_backward",
+    "bbd_u8_to_f32", "bbd_loss_combine_forward", "bbd_loss_combine_backward", "bbd_pack_rgba",
 ]
 
 
@@ -129,6 +130,6 @@ def cuda_backend() -> Backend:
         if not torch.cuda.is_available():
             raise RuntimeError("bbd: no CUDA device; the view-synthesis loss has no CPU implementation")
         _CUDA = Backend(LIB_PATH, "bbd_", cuda=True)
-        if _CUDA.dll.bbd_version() != 1:
+        if _CUDA.dll.bbd_version() != 2:
             raise RuntimeError("bbd: ABI version mismatch; rebuild libbbd_loss.so")
     return _CUDA

@@ -11,6 +11,7 @@
 #include "bbd_ops.cuh"
 #include "bbd_smooth.cuh"
 #include "bbd_strip.cuh"
+#include "bbd_stream.cuh"
 
 namespace bbd {
 
@@ -194,11 +195,54 @@ __global__ void __launch_bounds__(SCfg::NT, BBD_MIN_BLOCKS) reproj_kernel(const 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// fused reprojection loss, streaming form (bbd_stream.cuh): one warp = one strip segment
+// ------------------------------------------------------------------------------------------
+#ifndef BBD_STREAM_WARPS
+#define BBD_STREAM_WARPS 2  // warps per block (independent units; a block is only a launch container)
+#endif
+#ifndef BBD_STREAM_MINB
+#define BBD_STREAM_MINB 4
+#endif
+template <int K, bool GRAD>
+__global__ void __launch_bounds__(BBD_STREAM_WARPS * 32, BBD_STREAM_MINB) reproj_stream_kernel(const bbd_reproj_args a, int n_units, int part_stride) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * BBD_STREAM_WARPS + warp;
+  if (unit >= n_units) return;  // warp-uniform
+  stream_unit<K, GRAD>(a, unit, lane, smem + (size_t)warp * StreamSmem<K>::FLOATS, part_stride);
+}
+
+// (n,3,H,W) -> (n,H,W,4): a thread converts four consecutive pixels (3 x 16 B in, 4 x 16 B out)
+__global__ void __launch_bounds__(256) pack_rgba_kernel(int n, int HW, const float* __restrict__ planar, float4* __restrict__ rgba) {
+  const int q = HW / 4;  // HW % 4 == 0 is checked by the launcher for this path
+  const size_t total = (size_t)n * q;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t img = i / q, j = i - img * q;
+    const float4* p = reinterpret_cast<const float4*>(planar + img * 3 * HW) + j;
+    const float4 r = p[0], g = p[q], b = p[2 * (size_t)q];
+    float4* o = rgba + img * HW + j * 4;
+    o[0] = make_float4(r.x, g.x, b.x, 0.0f);
+    o[1] = make_float4(r.y, g.y, b.y, 0.0f);
+    o[2] = make_float4(r.z, g.z, b.z, 0.0f);
+    o[3] = make_float4(r.w, g.w, b.w, 0.0f);
+  }
+}
+__global__ void __launch_bounds__(256) pack_rgba_scalar_kernel(int n, int HW, const float* __restrict__ planar, float4* __restrict__ rgba) {
+  const size_t total = (size_t)n * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t img = i / HW, j = i - img * HW;
+    const float* p = planar + img * 3 * HW + j;
+    rgba[i] = make_float4(p[0], p[HW], p[2 * (size_t)HW], 0.0f);
+  }
+}
+
 // Sum the per-tile partials in a fixed order.  grid.x = S * (1 + num_pose); block 0..S-1 -> loss.
 // 768 threads = 64 tile-lanes x 12 components: every thread adds its share of the partials, a
 // fixed-order tail adds the lanes (deterministic, no atomics).
 constexpr int FIN_NT = 768, FIN_LANES = FIN_NT / 12;
-__global__ void __launch_bounds__(FIN_NT) reproj_finalize_kernel(const bbd_reproj_args a, float* loss, float* gpose, int ntiles) {
+__global__ void __launch_bounds__(FIN_NT) reproj_finalize_kernel(const bbd_reproj_args a, float* loss, float* gpose, int ntiles, int used) {
   __shared__ float red[FIN_NT];
   __shared__ float red2[32];
   const int tid = threadIdx.x;
@@ -207,7 +251,11 @@ __global__ void __launch_bounds__(FIN_NT) reproj_finalize_kernel(const bbd_repro
     const int s = blockIdx.x;
     const float* p = a.loss_part + (size_t)s * a.batch * ntiles;
     float acc = 0.0f;
-    for (int i = tid; i < a.batch * ntiles; i += FIN_NT) acc += p[i];
+    if (used == ntiles) {
+      for (int i = tid; i < a.batch * ntiles; i += FIN_NT) acc += p[i];
+    } else {
+      for (int i = tid; i < a.batch * used; i += FIN_NT) acc += p[(i / used) * ntiles + (i % used)];
+    }
     red[tid] = acc;
     __syncthreads();
     if (tid < 32) {
@@ -233,7 +281,7 @@ __global__ void __launch_bounds__(FIN_NT) reproj_finalize_kernel(const bbd_repro
     for (int k = 0; k < n_rep; ++k) {
       if (a.tab.rep[((size_t)b * BBD_MAX_REP + k) * 4 + 2] != pose) continue;
       const float* p = a.gpose_part + (((size_t)s * a.batch + b) * BBD_MAX_REP + k) * ntiles * 12;
-      for (int tI = lane; tI < ntiles; tI += FIN_LANES) acc += p[(size_t)tI * 12 + comp];
+      for (int tI = lane; tI < used; tI += FIN_LANES) acc += p[(size_t)tI * 12 + comp];
     }
   }
   red[tid] = acc;
@@ -534,14 +582,46 @@ static int grid_for(size_t total, int block) {
 
 using namespace bbd;
 
+static int tile_parts(int height, int width) {
+  return ((width + SCfg::TW - 1) / SCfg::TW) * ((height + SCfg::TH - 1) / SCfg::TH);
+}
+// slots per (scale, sample) in loss_part / gpose_part: enough for either kernel
+extern "C" int bbd_reproj_tiles(int32_t height, int32_t width) { return std::max(tile_parts(height, width), StreamGeo::units(height, width)); }
+
+// Which kernel serves these arguments (the finalize step must agree with the fused launch).
+static bool use_stream(const bbd_reproj_args* a) {
+  if (a->force_tile || a->min_rep < 1 || a->max_rep > 2) return false;
+  bool any = false;
+  for (int f = 0; f < BBD_MAX_FRAMES; ++f) {
+    if (a->frames[f] && !a->frames_rgba[f]) return false;
+    any = any || a->frames_rgba[f];
+  }
+  return any;
+}
+static int parts_used(const bbd_reproj_args* a) {
+  return use_stream(a) ? StreamGeo::units(a->height, a->width) : tile_parts(a->height, a->width);
+}
+
+template <int K, bool GRAD>
+static int launch_stream(const bbd_reproj_args* a, cudaStream_t stream) {
+  static bool configured = false;
+  constexpr size_t smem = (size_t)BBD_STREAM_WARPS * StreamSmem<K>::FLOATS * sizeof(float);
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(reproj_stream_kernel<K, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "reproj_stream_kernel: shared memory attribute");
+    configured = true;
+  }
+  const int n_units = a->num_scales * a->batch * StreamGeo::units(a->height, a->width);
+  const int blocks = (n_units + BBD_STREAM_WARPS - 1) / BBD_STREAM_WARPS;
+  reproj_stream_kernel<K, GRAD><<<blocks, BBD_STREAM_WARPS * 32, smem, stream>>>(*a, n_units, bbd_reproj_tiles(a->height, a->width));
+  return check_launch("reproj_stream_kernel");
+}
+
+
 extern "C" {
 
 int bbd_version(void) { return BBD_ABI_VERSION; }
 const char* bbd_last_error_string(void) { return g_err; }
-
-int bbd_reproj_tiles(int32_t height, int32_t width) {
-  return ((width + SCfg::TW - 1) / SCfg::TW) * ((height + SCfg::TH - 1) / SCfg::TH);
-}
 
 int bbd_ident_forward(const bbd_ident_args* a, bbd_stream_t stream) {
   if (!a || !a->target || !a->ident_min || !a->tab.hdr || !a->tab.ident) return fail(BBD_E_ARG, "ident: null argument");
@@ -559,6 +639,11 @@ int bbd_reproj_fused(const bbd_reproj_args* a, bbd_stream_t stream) {
   if (a->need_grad && (!a->gpose_part || !a->gdepth)) return fail(BBD_E_ARG, "reproj: gradient buffers missing");
   if (a->batch <= 0 || a->height < 2 || a->width < 2 || a->num_scales <= 0) return fail(BBD_E_ARG, "reproj: bad size");
   if (a->max_rep < 1 || a->max_rep > BBD_MAX_REP) return fail(BBD_E_RANGE, "reproj: max_rep out of range");
+  if (use_stream(a)) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->max_rep == 1) return a->need_grad ? launch_stream<1, true>(a, st) : launch_stream<1, false>(a, st);
+    return a->need_grad ? launch_stream<2, true>(a, st) : launch_stream<2, false>(a, st);
+  }
   // keep every candidate's warped tile resident while that still allows three blocks per SM
   const bool keep = StripSmem<SCfg>::floats(a->max_rep) * sizeof(float) <= 75 * 1024;
   const size_t smem = StripSmem<SCfg>::floats(keep ? a->max_rep : 1) * sizeof(float);
@@ -581,7 +666,7 @@ int bbd_reproj_finalize(const bbd_reproj_args* a, float* loss, float* gpose, bbd
   if (gpose && !a->gpose_part) return fail(BBD_E_ARG, "finalize: no pose partials");
   const int ntiles = bbd_reproj_tiles(a->height, a->width);
   const int blocks = a->num_scales * (1 + (gpose ? a->num_pose : 0));
-  reproj_finalize_kernel<<<blocks, FIN_NT, 0, (cudaStream_t)stream>>>(*a, loss, gpose, ntiles);
+  reproj_finalize_kernel<<<blocks, FIN_NT, 0, (cudaStream_t)stream>>>(*a, loss, gpose, ntiles, parts_used(a));
   return check_launch("reproj_finalize_kernel");
 }
 
@@ -785,6 +870,18 @@ int bbd_loss_combine_backward(int32_t n, const float* g_total, const float* g_pe
   if (n < 1 || n > BBD_MAX_SCALES || !(num_scales > 0.0f)) return fail(BBD_E_RANGE, "loss_combine: bad term count");
   loss_combine_grad_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(n, g_total, g_per_scale, weight, num_scales, g_reproj, g_smooth);
   return check_launch("loss_combine_grad_kernel");
+}
+
+int bbd_pack_rgba(int32_t n, int32_t height, int32_t width, const float* planar, float* rgba, bbd_stream_t stream) {
+  if (!planar || !rgba) return fail(BBD_E_ARG, "pack_rgba: null argument");
+  if (n <= 0) return 0;
+  const int HW = height * width;
+  const bool vec = (HW % 4 == 0) && ((uintptr_t)planar % 16 == 0) && ((uintptr_t)rgba % 16 == 0);
+  if (vec)
+    pack_rgba_kernel<<<grid_for((size_t)n * HW / 4, 256), 256, 0, (cudaStream_t)stream>>>(n, HW, planar, reinterpret_cast<float4*>(rgba));
+  else
+    pack_rgba_scalar_kernel<<<grid_for((size_t)n * HW, 256), 256, 0, (cudaStream_t)stream>>>(n, HW, planar, reinterpret_cast<float4*>(rgba));
+  return check_launch("pack_rgba_kernel");
 }
 
 int bbd_u8_to_f32(const uint8_t* src, float* dst, size_t n, bbd_stream_t stream) {

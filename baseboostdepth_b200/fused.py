@@ -28,6 +28,9 @@ import os as _os
 
 # BBD_SIDE_STREAMS=0 keeps every kernel on the launch stream (debugging / A-B measurements)
 _USE_SIDE = _os.environ.get("BBD_SIDE_STREAMS", "1") != "0"
+# BBD_FORCE_TILE=1 pins the round-1 tile kernel (every elementary operation rounded like the reference's
+# separate ATen kernels) instead of the streaming kernel with contracted / separable arithmetic
+_FORCE_TILE = _os.environ.get("BBD_FORCE_TILE", "0") != "0"
 _SIDE: Dict = {}
 
 
@@ -66,6 +69,27 @@ def _frame_ptrs(plan: LossPlan, frames: Dict, height, width):
         keep.append(t)
         arr[slot] = t.data_ptr() if t.numel() else None
     return arr, keep
+
+
+def stream_eligible(plan: LossPlan) -> bool:
+    """The streaming kernel handles one or two warped candidates per sample (plain +-m / stereo batches)."""
+    n = [len(r) for r in plan.rep]
+    return (not _FORCE_TILE) and min(n) >= 1 and max(n) <= 2
+
+
+def pack_frames(be, plan: LossPlan, keep, height, width):
+    """Channel-interleaved copies of the frame stacks (``bbd_pack_rgba``): one 16-byte load then fetches a
+    bilinear tap of all three channels.  Returns the pointer table and the tensors that own the memory."""
+    arr = (C.c_void_p * _lib.MAX_FRAMES)()
+    owned = []
+    for slot, t in enumerate(keep):
+        if not t.numel():
+            continue
+        out = torch.empty(t.shape[0], height, width, 4, device=t.device, dtype=torch.float32)
+        be.call("pack_rgba", t.shape[0], height, width, C.c_void_p(t.data_ptr()), C.c_void_p(out.data_ptr()))
+        owned.append(out)
+        arr[slot] = out.data_ptr()
+    return arr, owned
 
 
 def disps_key(disps):
@@ -164,6 +188,7 @@ class _FusedLoss(torch.autograd.Function):
         inv_K = inv_K.contiguous()
         tab = _tables(plan, dev)
         frame_arr, keep = _frame_ptrs(plan, frames, H, W)
+        rgba_arr, rgba_keep = pack_frames(be, plan, keep, H, W) if stream_eligible(plan) else (None, [])
 
         # 1 + 5. disparity -> depth and smoothness: on the helper stream (started here unless the caller
         # already did, see start_side_branch)
@@ -210,6 +235,9 @@ class _FusedLoss(torch.autograd.Function):
         ra.inv_K, ra.P, ra.ident_min, ra.tab = inv_K.data_ptr(), Pc.data_ptr(), ident_min.data_ptr(), tab
         ra.loss_part, ra.gpose_part, ra.gdepth = loss_part.data_ptr(), _lib.ptr(gpose_part), _lib.ptr(gdepth)
         ra.winner, ra.ident_arg = _lib.ptr(winner), _lib.ptr(ident_arg)
+        if rgba_arr is not None:
+            ra.frames_rgba = rgba_arr
+        ra.min_rep, ra.force_tile = min(len(r) for r in plan.rep), int(_FORCE_TILE)
         timers = cfg.get("timers")
         if timers is not None and be.cuda:
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -227,6 +255,7 @@ class _FusedLoss(torch.autograd.Function):
 
         ctx.cfg = cfg
         ctx.d2d = d2d
+        del rgba_keep   # consumed by the fused kernel (stream-ordered: the allocator may reuse it from here on)
         ctx.keep = (disps_c, depth, gdepth, gpose, gsm)
         ctx.aux = {"depth": depth, "ident_min": ident_min, "ident_arg": ident_arg, "winner": winner}
         cfg["aux"] = ctx.aux

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BBD_ABI_VERSION 1
+#define BBD_ABI_VERSION 2
 #define BBD_MAX_FRAMES 16 /* image stacks: frames -7..7 and 's' */
 #define BBD_MAX_GROUPS 8  /* noise stacks: one per baseline group */
 #define BBD_MAX_REP 12    /* warped candidates per target sample (x_min_opt, decomp) */
@@ -103,8 +103,17 @@ typedef struct bbd_reproj_args {
   float* gdepth;      /* (S,B,H,W) d mean_s / d depth_s;        may be NULL if !need_grad */
   uint8_t* winner;    /* (S,B,H,W) argmin index in candidate order (reproj..., then ident...); may be NULL */
   const uint8_t* ident_arg; /* (B,H,W); only read when winner != NULL */
+  /* Optional channel-interleaved copies of the frame stacks, (n_f,H,W,4) = r,g,b,0 per pixel, written by
+   * bbd_pack_rgba: one 16-byte load fetches a bilinear tap of all three channels.  When every stack
+   * that the tables reference has one, and 1 <= min_rep <= max_rep <= 2, bbd_reproj_fused runs the
+   * streaming kernel (csrc/bbd_stream.cuh); otherwise the tile kernel, which reads `frames`. */
+  const float* frames_rgba[BBD_MAX_FRAMES];
+  int32_t min_rep;    /* min n_rep over the batch (0 = unknown: tile kernel) */
+  int32_t force_tile; /* != 0: always the tile kernel (exact-rounding arithmetic), for A/B measurements */
 } bbd_reproj_args;
-int bbd_reproj_tiles(int32_t height, int32_t width); /* tiles per (scale, sample) */
+int bbd_reproj_tiles(int32_t height, int32_t width); /* partial-sum slots per (scale, sample) */
+/* (n,3,H,W) planar -> (n,H,W,4) interleaved, 4th component 0: the gather layout of the streaming kernel. */
+int bbd_pack_rgba(int32_t n, int32_t height, int32_t width, const float* planar, float* rgba, bbd_stream_t stream);
 int bbd_reproj_fused(const bbd_reproj_args* a, bbd_stream_t stream);
 /* loss (S) = sum(loss_part)/(B*H*W); gpose (S,num_pose,3,4) = sum over tiles. */
 int bbd_reproj_finalize(const bbd_reproj_args* a, float* loss, float* gpose, bbd_stream_t stream);

@@ -12,9 +12,12 @@
 
 #include <vector>
 
+#define BBD_EMU 1
+#include "simt.h"
 #include "../../baseboostdepth_b200/csrc/bbd_ops.cuh"
 #include "../../baseboostdepth_b200/csrc/bbd_smooth.cuh"
 #include "../../baseboostdepth_b200/csrc/bbd_strip.cuh"
+#include "../../baseboostdepth_b200/csrc/bbd_stream.cuh"
 
 using namespace bbd;
 #ifndef BBD_TILE_H
@@ -40,9 +43,50 @@ long emu_div_const_mismatches(float d) {
   return bad;
 }
 
-int emu_reproj_tiles(int32_t height, int32_t width) {
+static int tile_parts(int height, int width) {
   return ((width + SCfg::TW - 1) / SCfg::TW) * ((height + SCfg::TH - 1) / SCfg::TH);
 }
+int emu_reproj_tiles(int32_t height, int32_t width) {
+  const int a = tile_parts(height, width), b = StreamGeo::units(height, width);
+  return a > b ? a : b;
+}
+// same choice as the launcher in bbd_kernels.cu
+static bool use_stream(const bbd_reproj_args* a) {
+  if (a->force_tile || a->min_rep < 1 || a->max_rep > 2) return false;
+  bool any = false;
+  for (int f = 0; f < BBD_MAX_FRAMES; ++f) {
+    if (a->frames[f] && !a->frames_rgba[f]) return false;
+    any = any || a->frames_rgba[f];
+  }
+  return any;
+}
+static int parts_used(const bbd_reproj_args* a) {
+  return use_stream(a) ? StreamGeo::units(a->height, a->width) : tile_parts(a->height, a->width);
+}
+
+int emu_pack_rgba(int32_t n, int32_t H, int32_t W, const float* planar, float* rgba) {
+  const size_t HW = (size_t)H * W;
+  for (size_t img = 0; img < (size_t)n; ++img)
+    for (size_t j = 0; j < HW; ++j) {
+      float* o = rgba + (img * HW + j) * 4;
+      o[0] = planar[img * 3 * HW + j];
+      o[1] = planar[img * 3 * HW + HW + j];
+      o[2] = planar[img * 3 * HW + 2 * HW + j];
+      o[3] = 0.0f;
+    }
+  return 0;
+}
+
+}  // extern "C"
+template <int K, bool GRAD>
+static void emu_stream(const bbd_reproj_args& a) {
+  const int n_units = a.num_scales * a.batch * StreamGeo::units(a.height, a.width);
+  const int stride = emu_reproj_tiles(a.height, a.width);
+  std::vector<float> smem(StreamSmem<K>::FLOATS);
+  for (int unit = 0; unit < n_units; ++unit)
+    simt::run_block(32, [&](int tid) { stream_unit<K, GRAD>(a, unit, tid, smem.data(), stride); });
+}
+extern "C" {
 
 int emu_ident_forward(const bbd_ident_args* ap) {
   const bbd_ident_args& a = *ap;
@@ -74,6 +118,11 @@ int emu_ident_forward(const bbd_ident_args* ap) {
 
 int emu_reproj_fused(const bbd_reproj_args* ap) {
   const bbd_reproj_args& a = *ap;
+  if (use_stream(ap)) {
+    if (a.max_rep == 1) { if (a.need_grad) emu_stream<1, true>(a); else emu_stream<1, false>(a); }
+    else { if (a.need_grad) emu_stream<2, true>(a); else emu_stream<2, false>(a); }
+    return 0;
+  }
   // the CPU harness runs the reuse (non-KEEP) variant for batches with more than two candidates,
   // like the launcher does
   const bool keep = StripSmem<SCfg>::floats(a.max_rep) * sizeof(float) <= 75 * 1024;
@@ -140,10 +189,10 @@ int emu_reproj_fused(const bbd_reproj_args* ap) {
 
 int emu_reproj_finalize(const bbd_reproj_args* ap, float* loss, float* gpose) {
   const bbd_reproj_args& a = *ap;
-  const int ntiles = emu_reproj_tiles(a.height, a.width);
+  const int ntiles = emu_reproj_tiles(a.height, a.width), used = parts_used(ap);
   for (int s = 0; s < a.num_scales; ++s) {
     float tot = 0.0f;
-    for (int i = 0; i < a.batch * ntiles; ++i) tot += a.loss_part[(size_t)s * a.batch * ntiles + i];
+    for (int i = 0; i < a.batch * used; ++i) tot += a.loss_part[(size_t)s * a.batch * ntiles + (size_t)(i / used) * ntiles + (i % used)];
     loss[s] = tot / ((float)a.batch * (float)a.height * (float)a.width);
   }
   if (!gpose) return 0;
@@ -156,7 +205,7 @@ int emu_reproj_finalize(const bbd_reproj_args* ap, float* loss, float* gpose) {
           for (int k = 0; k < n_rep; ++k) {
             if (a.tab.rep[((size_t)b * BBD_MAX_REP + k) * 4 + 2] != pose) continue;
             const float* p = a.gpose_part + (((size_t)s * a.batch + b) * BBD_MAX_REP + k) * ntiles * 12;
-            for (int tI = 0; tI < ntiles; ++tI) acc += p[(size_t)tI * 12 + c];
+            for (int tI = 0; tI < used; ++tI) acc += p[(size_t)tI * 12 + c];
           }
         }
         gpose[((size_t)s * a.num_pose + pose) * 12 + c] = acc;

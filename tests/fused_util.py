@@ -19,9 +19,9 @@ def emu_backend() -> _lib.Backend:
     if _EMU is None:
         so, src = os.path.join(EMU_DIR, "libbbd_emu.so"), os.path.join(EMU_DIR, "bbd_emu.cpp")
         csrc = os.path.join(os.path.dirname(EMU_DIR), "..", "baseboostdepth_b200", "csrc")
-        deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc)]
+        deps = [src, os.path.join(EMU_DIR, "simt.h")] + [os.path.join(csrc, f) for f in os.listdir(csrc)]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-            subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, src],
+            subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-mfma", "-shared", "-fPIC", "-o", so, src],
                            check=True)
         _EMU = _lib.Backend(so, "emu_", cuda=False)
     return _EMU

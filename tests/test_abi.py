@@ -31,7 +31,7 @@ def test_library_exports_every_symbol(lib_path):
     dll = ctypes.CDLL(lib_path)
     for sym in declared_symbols():
         assert hasattr(dll, sym), sym
-    assert dll.bbd_version() == 1
+    assert dll.bbd_version() == 2
     dll.bbd_reproj_tiles.restype = ctypes.c_int
     assert dll.bbd_reproj_tiles(192, 640) == 23 * 12      # 28x16 tiles
 
