@@ -63,7 +63,7 @@ EXPORTS = [
     "bbd_backproject_backward", "bbd_project_forward", "bbd_project_chunks", "bbd_project_backward",
     "bbd_ssim_forward", "bbd_ssim_backward", "bbd_pose_pack_forward", "bbd_pose_pack_backward",
     "bbd_pose_forward", "bbd_pose_backward", "bbd_grid_sample_forward", "bbd_grid_sample_backward",
-    "bbd_u8_to_f32", "bbd_loss_combine_forward", "bbd_loss_combine_backward", "bbd_pack_rgba",
+    "bbd_u8_to_f32", "bbd_loss_combine_forward", "bbd_loss_combine_backward", "bbd_pack_rgba", "bbd_project_coords",
 ]
 
 

@@ -200,10 +200,11 @@ __global__ void __launch_bounds__(SCfg::NT, BBD_MIN_BLOCKS) reproj_kernel(const 
 // fused reprojection loss, streaming form (bbd_stream.cuh): one warp = one strip segment
 // ------------------------------------------------------------------------------------------
 #ifndef BBD_STREAM_WARPS
-#define BBD_STREAM_WARPS 2  // warps per block (independent units; a block is only a launch container)
+#define BBD_STREAM_WARPS 1  // one warp per block: every branch on the unit index is provably warp-uniform,
+                            // so the shuffles need no WARPSYNC / ENDCOLLECTIVE brackets
 #endif
 #ifndef BBD_STREAM_MINB
-#define BBD_STREAM_MINB 4
+#define BBD_STREAM_MINB 8
 #endif
 template <int K, bool GRAD>
 __global__ void __launch_bounds__(BBD_STREAM_WARPS * 32, BBD_STREAM_MINB) reproj_stream_kernel(const bbd_reproj_args a, int n_units, int part_stride) {
@@ -212,6 +213,13 @@ __global__ void __launch_bounds__(BBD_STREAM_WARPS * 32, BBD_STREAM_MINB) reproj
   const int unit = blockIdx.x * BBD_STREAM_WARPS + warp;
   if (unit >= n_units) return;  // warp-uniform
   stream_unit<K, GRAD>(a, unit, lane, smem + (size_t)warp * StreamSmem<K>::FLOATS, part_stride);
+}
+
+__global__ void stream_coords_kernel(int n, int H, int W, const float* depth, const float* inv_K, const float* P, float* grid,
+                                     float* pix) {
+  const size_t total = (size_t)n * H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    stream_coords_px(H, W, depth, inv_K, P, (int)(i / ((size_t)H * W)), (int)((i / W) % H), (int)(i % W), grid, pix);
 }
 
 // (n,3,H,W) -> (n,H,W,4): a thread converts four consecutive pixels (3 x 16 B in, 4 x 16 B out)
@@ -870,6 +878,15 @@ int bbd_loss_combine_backward(int32_t n, const float* g_total, const float* g_pe
   if (n < 1 || n > BBD_MAX_SCALES || !(num_scales > 0.0f)) return fail(BBD_E_RANGE, "loss_combine: bad term count");
   loss_combine_grad_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(n, g_total, g_per_scale, weight, num_scales, g_reproj, g_smooth);
   return check_launch("loss_combine_grad_kernel");
+}
+
+int bbd_project_coords(int32_t n, int32_t height, int32_t width, const float* depth, const float* inv_K, const float* P,
+                       float* grid, float* pix, bbd_stream_t stream) {
+  if (!depth || !inv_K || !P || (!grid && !pix)) return fail(BBD_E_ARG, "project_coords: null argument");
+  if (n <= 0) return 0;
+  stream_coords_kernel<<<grid_for((size_t)n * height * width, 256), 256, 0, (cudaStream_t)stream>>>(n, height, width, depth, inv_K,
+                                                                                                   P, grid, pix);
+  return check_launch("stream_coords_kernel");
 }
 
 int bbd_pack_rgba(int32_t n, int32_t height, int32_t width, const float* planar, float* rgba, bbd_stream_t stream) {

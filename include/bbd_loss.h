@@ -112,6 +112,12 @@ typedef struct bbd_reproj_args {
   int32_t force_tile; /* != 0: always the tile kernel (exact-rounding arithmetic), for A/B measurements */
 } bbd_reproj_args;
 int bbd_reproj_tiles(int32_t height, int32_t width); /* partial-sum slots per (scale, sample) */
+/* The projection chain of the streaming kernel on its own (parity instrumentation): for sample i < n, with
+ * inv_K row i and P row i, grid (n,2,H,W) = what Project3D.forward returns (layers.py:181-195, permuted),
+ * pix (n,2,H,W) = the clipped source coordinates of F.grid_sample (align_corners=True, border); floor(pix)
+ * is the north-west bilinear tap.  Either output may be NULL. */
+int bbd_project_coords(int32_t n, int32_t height, int32_t width, const float* depth, const float* inv_K, const float* P,
+                       float* grid, float* pix, bbd_stream_t stream);
 /* (n,3,H,W) planar -> (n,H,W,4) interleaved, 4th component 0: the gather layout of the streaming kernel. */
 int bbd_pack_rgba(int32_t n, int32_t height, int32_t width, const float* planar, float* rgba, bbd_stream_t stream);
 int bbd_reproj_fused(const bbd_reproj_args* a, bbd_stream_t stream);

@@ -64,6 +64,13 @@ static int parts_used(const bbd_reproj_args* a) {
   return use_stream(a) ? StreamGeo::units(a->height, a->width) : tile_parts(a->height, a->width);
 }
 
+int emu_project_coords(int32_t n, int32_t H, int32_t W, const float* depth, const float* inv_K, const float* P, float* grid,
+                       float* pix) {
+  for (int b = 0; b < n; ++b)
+    for (int i = 0; i < H * W; ++i) stream_coords_px(H, W, depth, inv_K, P, b, i / W, i % W, grid, pix);
+  return 0;
+}
+
 int emu_pack_rgba(int32_t n, int32_t H, int32_t W, const float* planar, float* rgba) {
   const size_t HW = (size_t)H * W;
   for (size_t img = 0; img < (size_t)n; ++img)

@@ -13,18 +13,23 @@ EMU_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
 _EMU = None
 
 
-def emu_backend() -> _lib.Backend:
-    """Compile (if stale) and load tests/emu/libbbd_emu.so -- the kernels' phase code run on the CPU."""
+def emu_backend(flags: str = None) -> _lib.Backend:
+    """Compile (if stale) and load tests/emu/libbbd_emu*.so -- the kernels' phase code run on the CPU.
+    ``flags`` (or $BBD_EMU_FLAGS): extra -D options selecting a kernel variant, built into its own file."""
     global _EMU
+    flags = os.environ.get("BBD_EMU_FLAGS", "") if flags is None else flags
     if _EMU is None:
-        so, src = os.path.join(EMU_DIR, "libbbd_emu.so"), os.path.join(EMU_DIR, "bbd_emu.cpp")
+        _EMU = {}
+    if flags not in _EMU:
+        tag = "".join(ch if ch.isalnum() else "_" for ch in flags)
+        so, src = os.path.join(EMU_DIR, f"libbbd_emu{tag}.so"), os.path.join(EMU_DIR, "bbd_emu.cpp")
         csrc = os.path.join(os.path.dirname(EMU_DIR), "..", "baseboostdepth_b200", "csrc")
         deps = [src, os.path.join(EMU_DIR, "simt.h")] + [os.path.join(csrc, f) for f in os.listdir(csrc)]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-            subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-mfma", "-shared", "-fPIC", "-o", so, src],
-                           check=True)
-        _EMU = _lib.Backend(so, "emu_", cuda=False)
-    return _EMU
+            subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-mfma", "-shared", "-fPIC"] + flags.split()
+                           + ["-o", so, src], check=True)
+        _EMU[flags] = _lib.Backend(so, "emu_", cuda=False)
+    return _EMU[flags]
 
 
 def run_fused(inputs, outputs, opt, noise, num_scales, backend=None, groups=None, want_winner=True):

@@ -110,7 +110,11 @@ def max_abs(a, b):
     return (a.detach().double().cpu() - b.detach().double().cpu()).abs().max().item() if a.numel() else 0.0
 
 
-def assert_grad_parity(mine, ref32, ref64, key, tol=1e-5):
+# every gradient comparison of a test session lands here; tests/conftest.py writes it out at session end
+PARITY_LOG = []
+
+
+def assert_grad_parity(mine, ref32, ref64, key, tol=1e-5, case=None):
     """Gradient parity bar.
 
     Primary: relative L2 error against the fp32 oracle <= 1e-5.  At full
@@ -118,13 +122,36 @@ def assert_grad_parity(mine, ref32, ref64, key, tol=1e-5):
     a single near-tie (argmin, |.| sign, border clip) that falls the other way moves an
     aggregated gradient by ~1/sqrt(N).  Where the primary bar is missed, the kernel must be
     no farther from the float64 evaluation than the fp32 oracle is (x2, + 2e-6).
+    Which bar applied is recorded in PARITY_LOG (and printed when it is the secondary one).
     """
     e = rel_l2(mine, ref32)
-    if e <= tol:
-        return e
     e_mine, e_ref = rel_l2(mine, ref64), rel_l2(ref32, ref64)
-    assert e_mine <= 2.0 * e_ref + 2e-6, (key, "vs fp32 oracle", e, "vs f64", e_mine, "oracle32 vs f64", e_ref)
+    bar = "rel_l2_vs_fp32_oracle<=%g" % tol if e <= tol else "no_farther_from_f64_than_fp32_oracle(x2+2e-6)"
+    ok = e <= tol or e_mine <= 2.0 * e_ref + 2e-6
+    PARITY_LOG.append({"case": case, "key": repr(key), "rel_l2_vs_fp32_oracle": e, "rel_l2_vs_f64": e_mine,
+                       "fp32_oracle_vs_f64": e_ref, "bar": bar, "passed": bool(ok)})
+    if e > tol:
+        print(f"[parity] secondary bar for {case} {key}: vs fp32 oracle {e:.3e}, vs f64 {e_mine:.3e}, "
+              f"oracle32 vs f64 {e_ref:.3e}")
+    assert ok, (key, "vs fp32 oracle", e, "vs f64", e_mine, "oracle32 vs f64", e_ref)
     return e
+
+
+def near_tie_mask(plan, aux, s, dilate=1):
+    """(B,H,W) bool: pixels whose best-vs-runner-up margin in the oracle is <= 1e-6, dilated by `dilate`
+    pixels (a selection that may legitimately differ changes the gradient of its 3x3 neighbourhood)."""
+    import torch.nn.functional as F
+    order = [b for grp in aux["groups"] for b in plan.group_members[grp]]
+    margins = []
+    for p in aux["planes"][s]:
+        top = torch.topk(-p, 2, dim=1).values
+        margins.append(top[:, 0] - top[:, 1])
+    margin = torch.cat(margins, 0)
+    near = torch.zeros_like(margin, dtype=torch.bool)
+    near[order] = margin <= 1e-6
+    if dilate:
+        near = F.max_pool2d(near.float().unsqueeze(1), 2 * dilate + 1, 1, dilate)[:, 0] > 0
+    return near
 
 
 def pixel_agreement(mine, ref32, tol=1e-5):
