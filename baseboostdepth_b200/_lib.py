@@ -27,7 +27,8 @@ class Tables(C.Structure):
 class IdentArgs(C.Structure):
     _fields_ = [("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("no_ssim", C.c_int32),
                 ("target", fp), ("frames", fp * MAX_FRAMES), ("noise", fp * MAX_GROUPS),
-                ("noise_scale", C.c_float), ("tab", Tables), ("ident_min", fp), ("ident_arg", fp)]
+                ("noise_scale", C.c_float), ("tab", Tables), ("ident_min", fp), ("ident_arg", fp),
+                ("frames_rgba", fp * MAX_FRAMES), ("force_tile", C.c_int32)]
 
 
 class ReprojArgs(C.Structure):

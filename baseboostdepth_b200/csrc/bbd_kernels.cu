@@ -222,6 +222,16 @@ __global__ void stream_coords_kernel(int n, int H, int W, const float* depth, co
     stream_coords_px(H, W, depth, inv_K, P, (int)(i / ((size_t)H * W)), (int)((i / W) % H), (int)(i % W), grid, pix);
 }
 
+// identity pre-pass, streaming form: one warp per block = one strip segment of one sample
+struct RgbaPtrs {
+  float* p[BBD_MAX_FRAMES];
+};
+__global__ void __launch_bounds__(32) ident_stream_kernel(const bbd_ident_args a, const RgbaPtrs rgba, int n_units) {
+  const int unit = blockIdx.x;
+  if (unit >= n_units) return;
+  ident_unit(a, rgba.p, unit, threadIdx.x);
+}
+
 // (n,3,H,W) -> (n,H,W,4): a thread converts four consecutive pixels (3 x 16 B in, 4 x 16 B out)
 __global__ void __launch_bounds__(256) pack_rgba_kernel(int n, int HW, const float* __restrict__ planar, float4* __restrict__ rgba) {
   const int q = HW / 4;  // HW % 4 == 0 is checked by the launcher for this path
@@ -634,6 +644,13 @@ const char* bbd_last_error_string(void) { return g_err; }
 int bbd_ident_forward(const bbd_ident_args* a, bbd_stream_t stream) {
   if (!a || !a->target || !a->ident_min || !a->tab.hdr || !a->tab.ident) return fail(BBD_E_ARG, "ident: null argument");
   if (a->batch <= 0 || a->height < 2 || a->width < 2) return fail(BBD_E_ARG, "ident: bad size");
+  if (!a->force_tile) {
+    RgbaPtrs rp;
+    for (int f = 0; f < BBD_MAX_FRAMES; ++f) rp.p[f] = a->frames_rgba[f];
+    const int n_units = a->batch * IdentGeo::units(a->height, a->width);
+    ident_stream_kernel<<<n_units, 32, 0, (cudaStream_t)stream>>>(*a, rp, n_units);
+    return check_launch("ident_stream_kernel");
+  }
   dim3 grid((a->width + SCfg::TW - 1) / SCfg::TW, (a->height + SCfg::TH - 1) / SCfg::TH, a->batch);
   const size_t smem = IdentStripSmem<SCfg>::floats() * sizeof(float);
   cudaFuncSetAttribute(ident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -77,16 +77,15 @@ def stream_eligible(plan: LossPlan) -> bool:
     return (not _FORCE_TILE) and min(n) >= 1 and max(n) <= 2
 
 
-def pack_frames(be, plan: LossPlan, keep, height, width):
-    """Channel-interleaved copies of the frame stacks (``bbd_pack_rgba``): one 16-byte load then fetches a
-    bilinear tap of all three channels.  Returns the pointer table and the tensors that own the memory."""
+def rgba_buffers(keep, height, width):
+    """Channel-interleaved copies of the frame stacks: one 16-byte load then fetches a bilinear tap of all
+    three channels.  Only allocated here; the identity pre-pass fills them while it reads the frames."""
     arr = (C.c_void_p * _lib.MAX_FRAMES)()
     owned = []
     for slot, t in enumerate(keep):
         if not t.numel():
             continue
         out = torch.empty(t.shape[0], height, width, 4, device=t.device, dtype=torch.float32)
-        be.call("pack_rgba", t.shape[0], height, width, C.c_void_p(t.data_ptr()), C.c_void_p(out.data_ptr()))
         owned.append(out)
         arr[slot] = out.data_ptr()
     return arr, owned
@@ -188,7 +187,7 @@ class _FusedLoss(torch.autograd.Function):
         inv_K = inv_K.contiguous()
         tab = _tables(plan, dev)
         frame_arr, keep = _frame_ptrs(plan, frames, H, W)
-        rgba_arr, rgba_keep = pack_frames(be, plan, keep, H, W) if stream_eligible(plan) else (None, [])
+        rgba_arr, rgba_keep = rgba_buffers(keep, H, W) if stream_eligible(plan) else (None, [])
 
         # 1 + 5. disparity -> depth and smoothness: on the helper stream (started here unless the caller
         # already did, see start_side_branch)
@@ -218,6 +217,9 @@ class _FusedLoss(torch.autograd.Function):
         ia.tab = tab
         ia.ident_min = ident_min.data_ptr()
         ia.ident_arg = _lib.ptr(ident_arg)
+        if rgba_arr is not None:
+            ia.frames_rgba = rgba_arr
+        ia.force_tile = int(_FORCE_TILE)
         be.call("ident_forward", C.byref(ia))
         for ev in join or ():
             torch.cuda.current_stream().wait_event(ev)

@@ -74,6 +74,12 @@ typedef struct bbd_ident_args {
   bbd_tables tab;
   float* ident_min;
   uint8_t* ident_arg;
+  /* Optional: (n_f,H,W,4) channel-interleaved copies of the frame stacks, written as a by-product (every
+   * source row passes through registers here anyway); the layout bbd_reproj_args.frames_rgba expects.
+   * NULL entries are skipped. */
+  float* frames_rgba[BBD_MAX_FRAMES];
+  int32_t force_tile; /* 0: streaming form (contracted / separable arithmetic); != 0: tile kernel with the
+                         reference's rounding, no copies written */
 } bbd_ident_args;
 int bbd_ident_forward(const bbd_ident_args* a, bbd_stream_t stream);
 

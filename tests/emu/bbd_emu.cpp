@@ -97,6 +97,12 @@ extern "C" {
 
 int emu_ident_forward(const bbd_ident_args* ap) {
   const bbd_ident_args& a = *ap;
+  if (!a.force_tile) {
+    const int n_units = a.batch * IdentGeo::units(a.height, a.width);
+    for (int unit = 0; unit < n_units; ++unit)
+      simt::run_block(32, [&](int tid) { ident_unit(a, const_cast<float* const*>(a.frames_rgba), unit, tid); });
+    return 0;
+  }
   std::vector<float> smem(IdentStripSmem<SCfg>::floats());
   std::vector<StripCtx> ctx(SCfg::NT);
   const int H = a.height, W = a.width;
