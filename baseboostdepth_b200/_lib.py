@@ -44,14 +44,14 @@ class SmoothArgs(C.Structure):
     _fields_ = [("batch", C.c_int32), ("levels", C.c_int32), ("h", C.c_int32 * MAX_SCALES),
                 ("w", C.c_int32 * MAX_SCALES), ("disp", fp * MAX_SCALES), ("img", fp * MAX_SCALES),
                 ("gdisp", fp * MAX_SCALES), ("scratch", fp), ("loss", fp), ("max_chunks", C.c_int32),
-                ("normalize", C.c_int32)]
+                ("normalize", C.c_int32), ("defer_norm", C.c_int32), ("coef", fp)]
 
 
 class D2DArgs(C.Structure):
     _fields_ = [("batch", C.c_int32), ("levels", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
                 ("h", C.c_int32 * MAX_SCALES), ("w", C.c_int32 * MAX_SCALES), ("min_disp", C.c_float),
                 ("disp_span", C.c_float), ("sql", C.c_int32), ("disp", fp * MAX_SCALES), ("depth", fp),
-                ("gdepth", fp), ("gscale", fp), ("gsmooth", fp * MAX_SCALES), ("gsmooth_scale", fp),
+                ("gdepth", fp), ("gscale", fp), ("gsmooth", fp * MAX_SCALES), ("gsmooth_scale", fp), ("gsmooth_coef", fp),
                 ("gdisp", fp * MAX_SCALES), ("scratch", fp)]
 
 
@@ -113,7 +113,7 @@ class Backend:
         if self.cuda:
             args = args + (self.stream(),)
         rc = fn(*args)
-        self.launches += {"smooth_fused": 3, "disp_to_depth_backward": 2}.get(name, 1)
+        self.launches += {"smooth_fused": 2, "disp_to_depth_backward": 2}.get(name, 1)
         if rc != 0:
             msg = self.dll.bbd_last_error_string().decode() if self.cuda else ""
             raise RuntimeError(f"bbd_{name} failed with code {rc}: {msg}")

@@ -325,51 +325,53 @@ __global__ void __launch_bounds__(SM_NT) smooth_stage1_kernel(const SmoothArgs a
   if (tid == 0) sm_slot(a, lvl, b, 0)[chunk] = sm_l2(red);
 }
 
-__global__ void __launch_bounds__(SM_NT) smooth_stage2_kernel(const SmoothArgs a) {
-  __shared__ float red[SM_NT + SM_NT / 16];
+// grid (column blocks, row chunks, levels * B); 4 warps x 30 owned columns per block.  The last block to
+// take a ticket reduces the partials (fixed order) to the level losses and the per-sample scalars.
+__global__ void __launch_bounds__(SMR_WARPS * 32) smooth_rows_kernel(const SmoothArgs a, float* coef, unsigned* ticket, unsigned total) {
+  __shared__ float red[SMR_WARPS][3];
   __shared__ float mean_s;
-  const int lvl = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
-  if (chunk >= sm_chunks(a.h[lvl], a.w[lvl])) return;
-  if (tid == 0) mean_s = sm_sample_mean(a, lvl, b);
+  __shared__ int last_s;
+  __shared__ float tx_s[BBD_MAX_SCALES * 256], ty_s[BBD_MAX_SCALES * 256];
+  const int lvl = blockIdx.z / a.batch, b = blockIdx.z - lvl * a.batch, bx = blockIdx.x, by = blockIdx.y;
+  const int nbx = smr_nbx(a.w[lvl]);
+  if (bx >= nbx || by >= smr_nby(a.h[lvl])) return;  // block-uniform
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) mean_s = a.normalize ? sm_sample_mean(a, lvl, b) : 0.0f;
   __syncthreads();
   float out[3];
-  sm_stage2_thread(a, lvl, b, chunk, tid, mean_s, out);
-  for (int k = 0; k < 3; ++k) {
-    sm_park(red, tid, out[k]);
-    __syncthreads();
-    sm_l1(red, tid);
-    __syncthreads();
-    if (tid == 0) sm_slot(a, lvl, b, 1 + k)[chunk] = sm_l2(red);
-    __syncthreads();
+  sm_rows_lane(a, lvl, b, bx, by, warp, lane, mean_s, out);
+  if (lane == 0) { red[warp][0] = out[0]; red[warp][1] = out[1]; red[warp][2] = out[2]; }
+  __syncthreads();
+  if (tid == 0) {
+    const int slot = by * nbx + bx;
+    for (int k = 0; k < 3; ++k) {
+      float v = 0.0f;
+      for (int w = 0; w < SMR_WARPS; ++w) v += red[w][k];
+      sm_slot(a, lvl, b, 1 + k)[slot] = v;
+    }
+    __threadfence();
+    last_s = (atomicAdd(ticket, 1u) == total - 1u) ? 1 : 0;
   }
+  __syncthreads();
+  if (!last_s) return;
+  __threadfence();
+  const int pairs = a.levels * a.batch;
+  for (int i = tid; i < pairs; i += blockDim.x) {
+    float sums[2];
+    sm_finish_sample(a, i / a.batch, i % a.batch, coef, sums);
+    tx_s[i] = sums[0];
+    ty_s[i] = sums[1];
+  }
+  __syncthreads();
+  if (tid < a.levels) a.loss[tid] = sm_level_loss(a, tid, tx_s + tid * a.batch, ty_s + tid * a.batch);
+  if (tid == 0) *ticket = 0u;  // ready for the next launch
 }
 
-__global__ void __launch_bounds__(SM_NT) smooth_stage3_kernel(const SmoothArgs a) {
-  __shared__ float red[SM_NT + SM_NT / 16];
-  __shared__ float mean_s, dot_s;
-  const int lvl = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
-  if (chunk >= sm_chunks(a.h[lvl], a.w[lvl])) return;
-  if (tid == 0) mean_s = sm_sample_mean(a, lvl, b);
-  if (tid == 32) dot_s = sm_sample_gd_dot(a, lvl, b);
-  __syncthreads();
-  sm_stage3_thread(a, lvl, b, chunk, tid, mean_s, dot_s);
-  if (b == 0 && chunk == 0) {
-    float out[2];
-    sm_loss_thread(a, lvl, tid, out);
-    float tot[2];
-    for (int k = 0; k < 2; ++k) {
-      sm_park(red, tid, out[k]);
-      __syncthreads();
-      sm_l1(red, tid);
-      __syncthreads();
-      tot[k] = sm_l2(red);
-      __syncthreads();
-    }
-    if (tid == 0) {
-      const float h = (float)a.h[lvl], w = (float)a.w[lvl], B = (float)a.batch;
-      a.loss[lvl] = tot[0] / (B * h * (w - 1.0f)) + tot[1] / (B * (h - 1.0f) * w);
-    }
-  }
+__global__ void __launch_bounds__(256) smooth_apply_kernel(const SmoothArgs a, const float* coef) {
+  const int lvl = blockIdx.z, b = blockIdx.y;
+  const int n = a.h[lvl] * a.w[lvl];
+  if (!a.gdisp[lvl]) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) sm_apply_px(a, coef, lvl, b, i);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -695,30 +697,50 @@ int bbd_reproj_finalize(const bbd_reproj_args* a, float* loss, float* gpose, bbd
   return check_launch("reproj_finalize_kernel");
 }
 
-size_t bbd_smooth_scratch_floats(int32_t batch, int32_t levels, const int32_t* h, const int32_t* w) {
+static int smooth_max_parts(int levels, const int32_t* h, const int32_t* w) {
   int mc = 1;
-  for (int l = 0; l < levels; ++l) {
-    const int c = sm_chunks(h[l], w[l]);
-    if (c > mc) mc = c;
-  }
-  return (size_t)levels * batch * 4 * mc;
+  for (int l = 0; l < levels; ++l) mc = std::max(mc, std::max(sm_chunks(h[l], w[l]), smr_blocks(h[l], w[l])));
+  return mc;
+}
+// partial-sum slots (levels,B,4,parts) + the per-sample scalars (levels,B,2) + the ticket of the last-block reduction
+size_t bbd_smooth_scratch_floats(int32_t batch, int32_t levels, const int32_t* h, const int32_t* w) {
+  return (size_t)levels * batch * 4 * smooth_max_parts(levels, h, w) + (size_t)levels * batch * 2 + 4;
 }
 
 int bbd_smooth_fused(const bbd_smooth_args* in, bbd_stream_t stream) {
   if (!in || !in->scratch || !in->loss) return fail(BBD_E_ARG, "smooth: null argument");
-  if (in->levels < 1 || in->levels > BBD_MAX_SCALES || in->batch <= 0) return fail(BBD_E_RANGE, "smooth: bad level count");
+  if (in->levels < 1 || in->levels > BBD_MAX_SCALES || in->batch <= 0 || in->batch > 256) return fail(BBD_E_RANGE, "smooth: bad level count / batch");
+  if (in->defer_norm && !in->coef) return fail(BBD_E_ARG, "smooth: defer_norm needs coef");
   bbd_smooth_args a = *in;
-  int mc = 1;
+  int nbx = 1, nby = 1;
+  unsigned total = 0;
   for (int l = 0; l < a.levels; ++l) {
     if (!a.disp[l] || !a.img[l] || a.h[l] < 2 || a.w[l] < 2) return fail(BBD_E_ARG, "smooth: bad level");
-    const int c = sm_chunks(a.h[l], a.w[l]);
-    if (c > mc) mc = c;
+    nbx = std::max(nbx, smr_nbx(a.w[l]));
+    nby = std::max(nby, smr_nby(a.h[l]));
+    total += (unsigned)(a.batch * smr_blocks(a.h[l], a.w[l]));
   }
+  const int mc = smooth_max_parts(a.levels, a.h, a.w);
   a.max_chunks = mc;
-  dim3 grid(mc, a.batch, a.levels);
-  smooth_stage1_kernel<<<grid, SM_NT, 0, (cudaStream_t)stream>>>(a);
-  smooth_stage2_kernel<<<grid, SM_NT, 0, (cudaStream_t)stream>>>(a);
-  smooth_stage3_kernel<<<grid, SM_NT, 0, (cudaStream_t)stream>>>(a);
+  float* tail = a.scratch + (size_t)a.levels * a.batch * 4 * mc;
+  float* coef = a.defer_norm ? a.coef : tail;
+  unsigned* ticket = reinterpret_cast<unsigned*>(tail + (size_t)a.levels * a.batch * 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(ticket, 0, sizeof(unsigned), st);
+  if (a.normalize) {
+    dim3 grid1(mc, a.batch, a.levels);
+    smooth_stage1_kernel<<<grid1, SM_NT, 0, st>>>(a);
+  }
+  dim3 grid(nbx, nby, a.levels * a.batch);
+  smooth_rows_kernel<<<grid, SMR_WARPS * 32, 0, st>>>(a, coef, ticket, total);
+  if (!a.defer_norm && a.normalize) {
+    bool any = false;
+    for (int l = 0; l < a.levels; ++l) any = any || a.gdisp[l];
+    if (any) {
+      dim3 grid3(8, a.batch, a.levels);
+      smooth_apply_kernel<<<grid3, 256, 0, st>>>(a, coef);
+    }
+  }
   return check_launch("smooth kernels");
 }
 

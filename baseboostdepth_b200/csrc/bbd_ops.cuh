@@ -210,7 +210,14 @@ BBD_HD float d2d_backward_px(const bbd_d2d_args& a, int lvl, int b, int iy, int 
     }
   }
   acc *= a.gscale[lvl];
-  if (a.gsmooth[lvl]) acc += a.gsmooth_scale[lvl] * a.gsmooth[lvl][((size_t)b * h + iy) * w + ix];
+  if (a.gsmooth[lvl]) {
+    float gs = a.gsmooth[lvl][((size_t)b * h + iy) * w + ix];
+    if (a.gsmooth_coef) {  // finish the deferred mean-normalisation of the smoothness gradient
+      const float* c = a.gsmooth_coef + ((size_t)lvl * a.batch + b) * 2;
+      gs = gs * c[0] - c[1];
+    }
+    acc += a.gsmooth_scale[lvl] * gs;
+  }
   return acc;
 }
 

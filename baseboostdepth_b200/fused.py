@@ -141,6 +141,10 @@ def start_side_branch(be, disps, pyramid, bhw, min_depth, max_depth, sql, need_g
     smooth = torch.empty(S, **f32)
     sa.scratch, sa.loss = scratch.data_ptr(), smooth.data_ptr()
     keep.append(scratch)
+    # the mean-normalisation of the smoothness gradient is finished by the disparity backward (one pass less)
+    coef = torch.empty(S, B, 2, **f32) if need_grad else None
+    if coef is not None:
+        sa.defer_norm, sa.coef = 1, coef.data_ptr()
 
     join = None
     if be.cuda and _USE_SIDE:
@@ -161,7 +165,7 @@ def start_side_branch(be, disps, pyramid, bhw, min_depth, max_depth, sql, need_g
         be.call("disp_to_depth_forward", C.byref(d2d))
         be.call("smooth_fused", C.byref(sa))
     return dict(disps=disps_key(disps), disps_c=disps_c, d2d=d2d, depth=depth, gsm=gsm, smooth=smooth, join=join,
-                keep=keep)
+                keep=keep, coef=coef)
 
 
 class _FusedLoss(torch.autograd.Function):
@@ -258,7 +262,7 @@ class _FusedLoss(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.d2d = d2d
         del rgba_keep   # consumed by the fused kernel (stream-ordered: the allocator may reuse it from here on)
-        ctx.keep = (disps_c, depth, gdepth, gpose, gsm)
+        ctx.keep = (disps_c, depth, gdepth, gpose, gsm, pre["coef"])
         ctx.aux = {"depth": depth, "ident_min": ident_min, "ident_arg": ident_arg, "winner": winner}
         cfg["aux"] = ctx.aux
         return reproj, smooth
@@ -267,7 +271,7 @@ class _FusedLoss(torch.autograd.Function):
     def backward(ctx, g_reproj, g_smooth):
         cfg = ctx.cfg
         be: _lib.Backend = cfg["backend"]
-        disps_c, depth, gdepth, gpose, gsm = ctx.keep
+        disps_c, depth, gdepth, gpose, gsm, coef = ctx.keep
         if gdepth is None:
             raise RuntimeError("bbd: fused loss was evaluated with need_grad=False")
         g_reproj = g_reproj.contiguous().float()
@@ -278,6 +282,7 @@ class _FusedLoss(torch.autograd.Function):
         d2d.gdepth = gdepth.data_ptr()
         d2d.gscale = g_reproj.data_ptr()
         d2d.gsmooth_scale = g_smooth.data_ptr()
+        d2d.gsmooth_coef = _lib.ptr(coef)
         for l, g in enumerate(gdisps):
             d2d.gdisp[l] = g.data_ptr()
             d2d.gsmooth[l] = gsm[l].data_ptr()

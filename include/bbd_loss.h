@@ -161,8 +161,8 @@ int bbd_warp_forward(int32_t n, int32_t height, int32_t width, const float* imag
 /* ---- edge-aware smoothness, forward + backward ----------------------------
  * trainer.py:560-563 + layers.py:203-216 for every pyramid level of a step:
  * d = disp / (mean_hw(disp) + 1e-7); loss = mean|dx d|e^{-mean_c|dx I|} + same in y.
- * Three enqueued stages (sample means; per-pixel terms and the coupling sum;
- * final gradient), each covering all levels.  loss[l] and gdisp[l] = d loss[l] / d disp_l
+ * Two enqueued stages (sample means; per-pixel terms, coupling sums and the level losses), each covering
+ * all levels, plus a small element-wise finish unless the caller defers it (defer_norm).  loss[l] and gdisp[l] = d loss[l] / d disp_l
  * are unweighted; the caller applies disparity_smoothness / 2^scale (trainer.py:564). */
 typedef struct bbd_smooth_args {
   int32_t batch, levels;
@@ -175,6 +175,10 @@ typedef struct bbd_smooth_args {
   int32_t max_chunks;                /* set by the library */
   int32_t normalize;                 /* 1: divide by the per-sample mean first (trainer.py:560-562);
                                         0: plain get_smooth_loss(disp, img) (layers.py:203-216) */
+  int32_t defer_norm;                /* 1: leave gdisp[l] = d loss / d(normalised disp) and write the two scalars per
+                                        (level, sample) that finish it, g_disp = g * coef[0] - coef[1], to `coef`;
+                                        bbd_disp_to_depth_backward applies them on the fly (gsmooth_coef) */
+  float* coef;                       /* (levels,B,2); required when defer_norm */
 } bbd_smooth_args;
 size_t bbd_smooth_scratch_floats(int32_t batch, int32_t levels, const int32_t* h, const int32_t* w);
 int bbd_smooth_fused(const bbd_smooth_args* a, bbd_stream_t stream);
@@ -198,6 +202,8 @@ typedef struct bbd_d2d_args {
   const float* gscale;               /* (S) device, backward only */
   const float* gsmooth[BBD_MAX_SCALES]; /* (B,1,h,w) optional extra term (smoothness gradient), or NULL */
   const float* gsmooth_scale;        /* (S) device: gdisp += gsmooth_scale[s] * gsmooth[s] */
+  const float* gsmooth_coef;         /* (S,B,2) or NULL: gsmooth[s] is first finished as g * coef[0] - coef[1]
+                                        (bbd_smooth_args.defer_norm) */
   float* gdisp[BBD_MAX_SCALES];      /* (B,1,h,w) backward only */
   float* scratch;                    /* backward only: bbd_d2d_scratch_floats() floats (row sums of the
                                         separable gather for the levels upsampled by 2, 4 or 8) */

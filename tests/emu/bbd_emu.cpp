@@ -226,64 +226,67 @@ int emu_reproj_finalize(const bbd_reproj_args* ap, float* loss, float* gpose) {
   return 0;
 }
 
-size_t emu_smooth_scratch_floats(int32_t batch, int32_t levels, const int32_t* h, const int32_t* w) {
+static int smooth_max_parts(int levels, const int32_t* h, const int32_t* w) {
   int mc = 1;
-  for (int l = 0; l < levels; ++l) mc = sm_chunks(h[l], w[l]) > mc ? sm_chunks(h[l], w[l]) : mc;
-  return (size_t)levels * batch * 4 * mc;
+  for (int l = 0; l < levels; ++l) {
+    const int c = sm_chunks(h[l], w[l]) > smr_blocks(h[l], w[l]) ? sm_chunks(h[l], w[l]) : smr_blocks(h[l], w[l]);
+    mc = c > mc ? c : mc;
+  }
+  return mc;
+}
+size_t emu_smooth_scratch_floats(int32_t batch, int32_t levels, const int32_t* h, const int32_t* w) {
+  return (size_t)levels * batch * 4 * smooth_max_parts(levels, h, w) + (size_t)levels * batch * 2 + 4;
 }
 
 int emu_smooth_fused(const bbd_smooth_args* in) {
   bbd_smooth_args a = *in;
-  int mc = 1;
-  for (int l = 0; l < a.levels; ++l) mc = sm_chunks(a.h[l], a.w[l]) > mc ? sm_chunks(a.h[l], a.w[l]) : mc;
+  const int mc = smooth_max_parts(a.levels, a.h, a.w);
   a.max_chunks = mc;
-  std::vector<float> red(SM_NT + SM_NT / 16);
-  auto block_sum = [&](std::vector<float>& vals) {
-    for (int tid = 0; tid < SM_NT; ++tid) sm_park(red.data(), tid, vals[tid]);
-    for (int tid = 0; tid < SM_NT; ++tid) sm_l1(red.data(), tid);
-    return sm_l2(red.data());
-  };
-  std::vector<float> v(SM_NT), v3(3 * SM_NT);
-  for (int lvl = 0; lvl < a.levels; ++lvl)
-    for (int b = 0; b < a.batch; ++b)
-      for (int c = 0; c < sm_chunks(a.h[lvl], a.w[lvl]); ++c) {
-        for (int tid = 0; tid < SM_NT; ++tid) v[tid] = sm_stage1_thread(a, lvl, b, c, tid);
-        sm_slot(a, lvl, b, 0)[c] = block_sum(v);
-      }
+  float* tail = a.scratch + (size_t)a.levels * a.batch * 4 * mc;
+  float* coef = a.defer_norm ? a.coef : tail;
+  std::vector<float> red(SM_NT + SM_NT / 16), v(SM_NT);
+  if (a.normalize)
+    for (int lvl = 0; lvl < a.levels; ++lvl)
+      for (int b = 0; b < a.batch; ++b)
+        for (int c = 0; c < sm_chunks(a.h[lvl], a.w[lvl]); ++c) {
+          for (int tid = 0; tid < SM_NT; ++tid) v[tid] = sm_stage1_thread(a, lvl, b, c, tid);
+          for (int tid = 0; tid < SM_NT; ++tid) sm_park(red.data(), tid, v[tid]);
+          for (int tid = 0; tid < SM_NT; ++tid) sm_l1(red.data(), tid);
+          sm_slot(a, lvl, b, 0)[c] = sm_l2(red.data());
+        }
+  // stage 2: one fiber block per warp of the device kernel's blocks
   for (int lvl = 0; lvl < a.levels; ++lvl)
     for (int b = 0; b < a.batch; ++b) {
-      const float mean = sm_sample_mean(a, lvl, b);
-      for (int c = 0; c < sm_chunks(a.h[lvl], a.w[lvl]); ++c) {
-        for (int tid = 0; tid < SM_NT; ++tid) {
-          float out[3];
-          sm_stage2_thread(a, lvl, b, c, tid, mean, out);
-          for (int k = 0; k < 3; ++k) v3[k * SM_NT + tid] = out[k];
+      const float mean = a.normalize ? sm_sample_mean(a, lvl, b) : 0.0f;
+      const int nbx = smr_nbx(a.w[lvl]), nby = smr_nby(a.h[lvl]);
+      for (int by = 0; by < nby; ++by)
+        for (int bx = 0; bx < nbx; ++bx) {
+          float tot[3] = {0.0f, 0.0f, 0.0f};
+          for (int warp = 0; warp < SMR_WARPS; ++warp) {
+            float out[3];
+            simt::run_block(32, [&](int tid) {
+              float o[3];
+              sm_rows_lane(a, lvl, b, bx, by, warp, tid, mean, o);
+              if (tid == 0) { out[0] = o[0]; out[1] = o[1]; out[2] = o[2]; }
+            });
+            for (int k = 0; k < 3; ++k) tot[k] += out[k];
+          }
+          for (int k = 0; k < 3; ++k) sm_slot(a, lvl, b, 1 + k)[by * nbx + bx] = tot[k];
         }
-        for (int k = 0; k < 3; ++k) {
-          for (int tid = 0; tid < SM_NT; ++tid) v[tid] = v3[k * SM_NT + tid];
-          sm_slot(a, lvl, b, 1 + k)[c] = block_sum(v);
-        }
-      }
     }
-  for (int lvl = 0; lvl < a.levels; ++lvl) {
-    for (int b = 0; b < a.batch; ++b) {
-      const float mean = sm_sample_mean(a, lvl, b);
-      const float gd_dot = sm_sample_gd_dot(a, lvl, b);
-      for (int c = 0; c < sm_chunks(a.h[lvl], a.w[lvl]); ++c)
-        for (int tid = 0; tid < SM_NT; ++tid) sm_stage3_thread(a, lvl, b, c, tid, mean, gd_dot);
-    }
-    float tot[2];
-    for (int k = 0; k < 2; ++k) {
-      for (int tid = 0; tid < SM_NT; ++tid) {
-        float out[2];
-        sm_loss_thread(a, lvl, tid, out);
-        v[tid] = out[k];
-      }
-      tot[k] = block_sum(v);
-    }
-    const float h = (float)a.h[lvl], w = (float)a.w[lvl], B = (float)a.batch;
-    a.loss[lvl] = tot[0] / (B * h * (w - 1.0f)) + tot[1] / (B * (h - 1.0f) * w);
+  std::vector<float> tx(a.levels * a.batch), ty(a.levels * a.batch);
+  for (int i = 0; i < a.levels * a.batch; ++i) {
+    float sums[2];
+    sm_finish_sample(a, i / a.batch, i % a.batch, coef, sums);
+    tx[i] = sums[0];
+    ty[i] = sums[1];
   }
+  for (int lvl = 0; lvl < a.levels; ++lvl) a.loss[lvl] = sm_level_loss(a, lvl, tx.data() + lvl * a.batch, ty.data() + lvl * a.batch);
+  if (!a.defer_norm && a.normalize)
+    for (int lvl = 0; lvl < a.levels; ++lvl)
+      if (a.gdisp[lvl])
+        for (int b = 0; b < a.batch; ++b)
+          for (int i = 0; i < a.h[lvl] * a.w[lvl]; ++i) sm_apply_px(a, coef, lvl, b, i);
   return 0;
 }
 
