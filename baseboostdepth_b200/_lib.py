@@ -64,7 +64,7 @@ EXPORTS = [
     "bbd_backproject_backward", "bbd_project_forward", "bbd_project_chunks", "bbd_project_backward",
     "bbd_ssim_forward", "bbd_ssim_backward", "bbd_pose_pack_forward", "bbd_pose_pack_backward",
     "bbd_pose_forward", "bbd_pose_backward", "bbd_grid_sample_forward", "bbd_grid_sample_backward",
-    "bbd_u8_to_f32", "bbd_loss_combine_forward", "bbd_loss_combine_backward", "bbd_pack_rgba", "bbd_project_coords",
+    "bbd_u8_to_f32", "bbd_loss_combine_forward", "bbd_loss_combine_backward", "bbd_pack_rgba", "bbd_project_coords", "bbd_reproj_kernel_name",
 ]
 
 
@@ -95,13 +95,25 @@ class Backend:
         getattr(self.dll, prefix + "d2d_scratch_floats").restype = C.c_size_t
         if cuda:
             self.dll.bbd_last_error_string.restype = C.c_char_p
+            self.dll.bbd_reproj_kernel_name.restype = C.c_char_p
 
     def check_device(self, *tensors):
+        dev = None
         for t in tensors:
             if t is None:
                 continue
             if self.cuda and not t.is_cuda:
                 raise RuntimeError("bbd: tensors must live on a CUDA device (there is no CPU path)")
+            if self.cuda:
+                # kernels are launched on torch's current device / stream with raw pointers: every tensor has
+                # to live there (one process drives one GPU; set it with torch.cuda.set_device)
+                if dev is None:
+                    dev = t.device
+                    if dev.index is not None and dev.index != torch.cuda.current_device():
+                        raise RuntimeError(f"bbd: tensors live on {dev} but the current CUDA device is "
+                                           f"cuda:{torch.cuda.current_device()} (call torch.cuda.set_device first)")
+                elif t.device != dev:
+                    raise RuntimeError(f"bbd: tensors on different devices ({dev} and {t.device})")
             if t.dtype not in (torch.float32, torch.int32, torch.uint8):
                 raise RuntimeError(f"bbd: unsupported dtype {t.dtype} (the path is fp32 only)")
 

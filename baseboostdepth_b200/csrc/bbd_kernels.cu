@@ -655,7 +655,12 @@ int bbd_ident_forward(const bbd_ident_args* a, bbd_stream_t stream) {
   }
   dim3 grid((a->width + SCfg::TW - 1) / SCfg::TW, (a->height + SCfg::TH - 1) / SCfg::TH, a->batch);
   const size_t smem = IdentStripSmem<SCfg>::floats() * sizeof(float);
-  cudaFuncSetAttribute(ident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static bool configured = false;  // the attribute sticks to the function: set once, checked
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "ident_kernel: shared memory attribute");
+    configured = true;
+  }
   ident_kernel<<<grid, SCfg::NT, smem, (cudaStream_t)stream>>>(*a);
   return check_launch("ident_kernel");
 }
@@ -676,16 +681,34 @@ int bbd_reproj_fused(const bbd_reproj_args* a, bbd_stream_t stream) {
   const size_t smem = StripSmem<SCfg>::floats(keep ? a->max_rep : 1) * sizeof(float);
   if (smem > 227 * 1024) return fail(BBD_E_RANGE, "reproj: shared memory budget exceeded");
   dim3 grid((a->width + SCfg::TW - 1) / SCfg::TW, (a->height + SCfg::TH - 1) / SCfg::TH, a->num_scales * a->batch);
-  auto launch = [&](auto kern) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t configured[4] = {0, 0, 0, 0};  // largest dynamic shared-memory size granted per variant
+  int rc = 0;
+  auto launch = [&](auto kern, int which) {
+    if (configured[which] < smem) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { rc = fail((int)e, "reproj_kernel: shared memory attribute"); return; }
+      configured[which] = smem;
+    }
     kern<<<grid, SCfg::NT, smem, (cudaStream_t)stream>>>(*a);
   };
   if (a->need_grad) {
-    if (keep) launch(reproj_kernel<true, true>); else launch(reproj_kernel<true, false>);
+    if (keep) launch(reproj_kernel<true, true>, 0); else launch(reproj_kernel<true, false>, 1);
   } else {
-    if (keep) launch(reproj_kernel<false, true>); else launch(reproj_kernel<false, false>);
+    if (keep) launch(reproj_kernel<false, true>, 2); else launch(reproj_kernel<false, false>, 3);
   }
+  if (rc) return rc;
   return check_launch("reproj_kernel");
+}
+
+const char* bbd_reproj_kernel_name(const bbd_reproj_args* a) {
+  if (!a) return "";
+  if (use_stream(a)) {
+    if (a->max_rep == 1) return a->need_grad ? "bbd::reproj_stream_kernel<1, 1>" : "bbd::reproj_stream_kernel<1, 0>";
+    return a->need_grad ? "bbd::reproj_stream_kernel<2, 1>" : "bbd::reproj_stream_kernel<2, 0>";
+  }
+  const bool keep = StripSmem<SCfg>::floats(a->max_rep) * sizeof(float) <= 75 * 1024;
+  if (a->need_grad) return keep ? "bbd::reproj_kernel<1, 1>" : "bbd::reproj_kernel<1, 0>";
+  return keep ? "bbd::reproj_kernel<0, 1>" : "bbd::reproj_kernel<0, 0>";
 }
 
 int bbd_reproj_finalize(const bbd_reproj_args* a, float* loss, float* gpose, bbd_stream_t stream) {

@@ -318,7 +318,7 @@ BBD_HD void rs_stats(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx&
       }
       // 0.85 * mean_c(ssim) + 0.15 * mean_c(l1), packed (same order as photometric_mix)
       const f2 loss = add(mul(bc2(BBD_W_SSIM), mul(ssim_sum, bc2(BBD_THIRD))), mul(bc2(BBD_W_L1), mul(l1_sum, bc2(BBD_THIRD))));
-      if (v0 && (k == 0 || loss.x < sm.best[j0])) {
+      if (v0 && (k == 0 || loss.x < sm.best[j0] || loss.x != loss.x)) {
         sm.best[j0] = loss.x;
         sm.bidx[j0] = k;
 #pragma unroll
@@ -328,7 +328,7 @@ BBD_HD void rs_stats(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx&
           sm.stash[(3 * c + 2) * C::R1N + j0] = wsxy[c].x;
         }
       }
-      if (v1 && (k == 0 || loss.y < sm.best[j1])) {
+      if (v1 && (k == 0 || loss.y < sm.best[j1] || loss.y != loss.y)) {
         sm.best[j1] = loss.y;
         sm.bidx[j1] = k;
 #pragma unroll
@@ -407,7 +407,7 @@ BBD_HD void rs_stats(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCtx&
       }
     }
     const float loss = photometric_mix(ssim_sum, l1_sum, a.no_ssim != 0);
-    if (k == 0 || loss < sm.best[j]) {
+    if (k == 0 || loss < sm.best[j] || loss != loss) {  // a NaN candidate wins, as in torch.min
       sm.best[j] = loss;
       sm.bidx[j] = k;
       if (!a.no_ssim) {
@@ -438,11 +438,11 @@ BBD_HD float rs_select(const bbd_reproj_args& a, StripSmem<C>& sm, const StripCt
       const size_t o = ((size_t)t.b * H + py) * W + t.px;
       const float idm = a.ident_min[o];
       const float bst = sm.best[j];
-      const bool rep_wins = bst <= idm;  // ties go to the lower index = the warped candidate
+      const bool rep_wins = !(bst > idm);  // ties go to the lower index = the warped candidate; so does NaN
       if (rep_wins) win = sm.bidx[j];
       const bool interior = t.lane >= 2 && t.lane <= 29 && i >= 1 && i <= C::TH;
       if (interior) {
-        part += rep_wins ? bst : idm;
+        part += (rep_wins && idm == idm) ? bst : idm;  // a NaN on either side reaches the mean (torch.min)
         if (a.winner)
           a.winner[(((size_t)t.s * a.batch + t.b) * H + py) * W + t.px] =
               (uint8_t)(rep_wins ? win : n_rep + (a.ident_arg ? a.ident_arg[o] : 0));
@@ -737,11 +737,11 @@ BBD_HD void is_candidate(const bbd_ident_args& a, IdentStripSmem<C>& sm, const S
       const f2 loss = add(mul(bc2(BBD_W_SSIM), mul(ssim_sum, bc2(BBD_THIRD))), mul(bc2(BBD_W_L1), mul(l1_sum, bc2(BBD_THIRD))));
       if (v0) {
         const float val = add(loss.x, mul(noise[py0 * W + t.u], a.noise_scale));
-        if (jcand == 0 || val < sm.best[j0]) { sm.best[j0] = val; sm.arg[j0] = jcand; }
+        if (jcand == 0 || val < sm.best[j0] || val != val) { sm.best[j0] = val; sm.arg[j0] = jcand; }
       }
       if (v1) {
         const float val = add(loss.y, mul(noise[py1 * W + t.u], a.noise_scale));
-        if (jcand == 0 || val < sm.best[j1]) { sm.best[j1] = val; sm.arg[j1] = jcand; }
+        if (jcand == 0 || val < sm.best[j1] || val != val) { sm.best[j1] = val; sm.arg[j1] = jcand; }
       }
     }
   }
@@ -773,7 +773,7 @@ BBD_HD void is_candidate(const bbd_ident_args& a, IdentStripSmem<C>& sm, const S
     }
     const float loss = photometric_mix(ssim_sum, l1_sum, a.no_ssim != 0);
     const float val = add(loss, mul(noise[py * W + t.u], a.noise_scale));
-    if (jcand == 0 || val < sm.best[j]) {
+    if (jcand == 0 || val < sm.best[j] || val != val) {
       sm.best[j] = val;
       sm.arg[j] = jcand;
     }

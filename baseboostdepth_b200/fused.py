@@ -44,6 +44,19 @@ def _side_streams(device):
     return s
 
 
+def _call(be, timers, key, name, *args):
+    """``be.call`` with an optional pair of CUDA events around it on the stream it is enqueued on
+    (bench.py's per-kernel table); ``timers[key]`` = (start, end)."""
+    if timers is None or not be.cuda:
+        be.call(name, *args)
+        return
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    be.call(name, *args)
+    t1.record()
+    timers[key] = (t0, t1)
+
+
 def _tables(plan: LossPlan, device):
     cache = getattr(plan, "_dev_tables", None)
     if cache is None or cache[0] != str(device):
@@ -96,7 +109,7 @@ def disps_key(disps):
     return tuple((d.data_ptr(), tuple(d.shape), d._version) for d in disps)
 
 
-def start_side_branch(be, disps, pyramid, bhw, min_depth, max_depth, sql, need_grad):
+def start_side_branch(be, disps, pyramid, bhw, min_depth, max_depth, sql, need_grad, timers=None):
     """Launch disparity -> depth (reference ``trainer.py:456`` + ``layers.py:13-22``) and the smoothness
     kernels (``trainer.py:560-564``) for one step.  They depend only on the disparities and the colour
     pyramid, are small and latency-bound, and therefore run on a helper stream between a fork and a
@@ -107,6 +120,14 @@ def start_side_branch(be, disps, pyramid, bhw, min_depth, max_depth, sql, need_g
     S = len(disps)
     assert 1 <= S <= _lib.MAX_SCALES
     be.check_device(*disps, *pyramid)
+    if need_grad:
+        # the transpose of the upsample is implemented for the pyramid the networks produce (integer factors
+        # up to 8); say so here rather than from inside autograd.backward
+        for d in disps:
+            h, w = d.shape[-2:]
+            if H % h or W % w or H // h > 8 or W // w > 8:
+                raise NotImplementedError(f"bbd: disparity level {tuple(d.shape[-2:])} is not an integer factor <= 8 "
+                                          f"of the frame {(H, W)}; gradients are only provided for such pyramids")
     dev = disps[0].device
     f32 = dict(device=dev, dtype=torch.float32)
     disps_c = [d.detach().contiguous() for d in disps]
@@ -155,15 +176,15 @@ def start_side_branch(be, disps, pyramid, bhw, min_depth, max_depth, sql, need_g
         for side, name, args in ((side_a, "smooth_fused", sa), (side_b, "disp_to_depth_forward", d2d)):
             side.wait_event(fork)
             with torch.cuda.stream(side):
-                be.call(name, C.byref(args))
+                _call(be, timers, name, name, C.byref(args))
                 ev = torch.cuda.Event()
                 ev.record(side)
                 join.append(ev)
         # (joining the smoothness kernels only after the fused kernel was measured: their tail then
         # competes with its first waves and costs it 9 us -- no net gain)
     else:
-        be.call("disp_to_depth_forward", C.byref(d2d))
-        be.call("smooth_fused", C.byref(sa))
+        _call(be, timers, "disp_to_depth_forward", "disp_to_depth_forward", C.byref(d2d))
+        _call(be, timers, "smooth_fused", "smooth_fused", C.byref(sa))
     return dict(disps=disps_key(disps), disps_c=disps_c, d2d=d2d, depth=depth, gsm=gsm, smooth=smooth, join=join,
                 keep=keep, coef=coef)
 
@@ -200,7 +221,7 @@ class _FusedLoss(torch.autograd.Function):
         pre = cfg.pop("pre", None)
         if pre is None or pre["disps"] != disps_key(disps) or (need_grad and not pre["gsm"]):
             pre = start_side_branch(be, disps, pyramid, (B, H, W), cfg["min_depth"], cfg["max_depth"], cfg["sql"],
-                                    need_grad)
+                                    need_grad, timers=cfg.get("timers"))
         disps_c, d2d, depth, gsm, smooth, join = (pre[k] for k in ("disps_c", "d2d", "depth", "gsm", "smooth", "join"))
         keep.extend(pre["keep"])
 
@@ -224,7 +245,7 @@ class _FusedLoss(torch.autograd.Function):
         if rgba_arr is not None:
             ia.frames_rgba = rgba_arr
         ia.force_tile = int(_FORCE_TILE)
-        be.call("ident_forward", C.byref(ia))
+        _call(be, cfg.get("timers"), "ident_forward", "ident_forward", C.byref(ia))
         for ev in join or ():
             torch.cuda.current_stream().wait_event(ev)
 
@@ -245,19 +266,15 @@ class _FusedLoss(torch.autograd.Function):
             ra.frames_rgba = rgba_arr
         ra.min_rep, ra.force_tile = min(len(r) for r in plan.rep), int(_FORCE_TILE)
         timers = cfg.get("timers")
+        _call(be, timers, "reproj_fused", "reproj_fused", C.byref(ra))
         if timers is not None and be.cuda:
-            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0.record()
-            be.call("reproj_fused", C.byref(ra))
-            t1.record()
-            timers["reproj_fused"] = (t0, t1)
-        else:
-            be.call("reproj_fused", C.byref(ra))
+            timers["reproj_kernel_name"] = be.dll.bbd_reproj_kernel_name(C.byref(ra)).decode()
 
         # 4. fixed-order reduction of the per-tile partials
         reproj = torch.empty(S, **f32)
         gpose = torch.empty(S, plan.n_pose, 3, 4, **f32) if need_grad else None
-        be.call("reproj_finalize", C.byref(ra), C.c_void_p(reproj.data_ptr()), C.c_void_p(_lib.ptr(gpose)))
+        _call(be, timers, "reproj_finalize", "reproj_finalize", C.byref(ra), C.c_void_p(reproj.data_ptr()),
+              C.c_void_p(_lib.ptr(gpose)))
 
         ctx.cfg = cfg
         ctx.d2d = d2d
@@ -291,6 +308,10 @@ class _FusedLoss(torch.autograd.Function):
         d2d.scratch = scratch.data_ptr()
         S = len(gdisps)
         full_res_first = S > 1 and tuple(disps_c[0].shape[-2:]) == tuple(depth.shape[-2:])
+        timers = cfg.get("timers")
+        if timers is not None and be.cuda:
+            tb0, tb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tb0.record()
         if be.cuda and full_res_first and _USE_SIDE:
             # pass 2 of a full-resolution level does not read the row sums of pass 1: it runs on a helper
             # stream next to pass 1, the remaining levels follow pass 1 on this stream
@@ -307,6 +328,9 @@ class _FusedLoss(torch.autograd.Function):
             main.wait_event(join)
         else:
             be.call("disp_to_depth_backward", C.byref(d2d))
+        if timers is not None and be.cuda:
+            tb1.record()
+            timers["disp_to_depth_backward"] = (tb0, tb1)
         return (None, gP) + tuple(gdisps)
 
 

@@ -12,7 +12,8 @@ critical path.
     step = GraphedLossStep(stager, make_io, opt, plan)
     slot = stager.upload_async()
     for ...:
-        nxt = stager.upload_async()          # next batch crosses PCIe during this step
+        fill(stager.host)                    # write the next batch (waits until that pinned arena is free)
+        nxt = stager.upload_async()          # ... which crosses PCIe during this step
         step.launch(slot)                    # replay; gradients land in step.grads(slot)
         loss_of_previous = step.collect()    # host float of the step launched before this one (or None)
         slot = nxt
@@ -20,6 +21,8 @@ critical path.
 
 ``make_io(views) -> (inputs, outputs, leaves)`` maps the stager's device views of one slot to the
 trainer's ``inputs`` / ``outputs`` dictionaries and names the tensors that need gradients.
+``prepare_inputs(inputs)`` (optional) does the same for ``inputs`` (e.g. the colour pyramid levels derived
+from the uploaded full-resolution frame instead of being uploaded).
 ``prepare(outputs)`` (optional) runs inside the captured step on a copy of ``outputs``: tensor ops that
 derive further entries from the uploaded ones, like the error-induced poses of ``--decomp``
 (``trainer.py:376-377``).
@@ -35,7 +38,7 @@ from .trainer import loss_step
 
 class GraphedLossStep:
     def __init__(self, stager, make_io: Callable, opt, plan, num_scales: Optional[int] = None, warmup: int = 3,
-                 prepare: Optional[Callable] = None):
+                 prepare: Optional[Callable] = None, prepare_inputs: Optional[Callable] = None):
         self.stager = stager
         self._graphs, self._loss, self._leaves = [], [], []
         n_slots = len(stager.dev_arena)
@@ -52,10 +55,12 @@ class GraphedLossStep:
             def run():
                 for p in leaves.values():
                     p.grad = None
-                outs = dict(outputs)
+                outs, ins = dict(outputs), dict(inputs)
                 if prepare is not None:                      # e.g. the decomp error poses, derived from T in-graph
                     prepare(outs)
-                losses = loss_step(inputs, outs, opt, plan, noise=None, num_scales=num_scales)
+                if prepare_inputs is not None:               # e.g. the colour pyramid, derived from the uploaded frame
+                    prepare_inputs(ins)
+                losses = loss_step(ins, outs, opt, plan, noise=None, num_scales=num_scales)
                 losses["loss"].backward()
                 return losses["loss"]
 

@@ -5,6 +5,12 @@ Here every tensor of the batch lives at a fixed offset of one pinned host arena,
 crosses PCIe as a single ``cudaMemcpyAsync`` on a side stream into one of two device arenas while
 the previous batch is still being consumed; the compute stream only waits on an event.  A
 ``DataLoader`` collate function can write straight into ``stager.host`` views.
+
+Host-side hazard (and how it is closed): a non-blocking DMA keeps *reading* its pinned source until it
+completes, so the host must not rewrite an arena whose upload is still in flight.  There is one pinned
+arena per device slot; ``stager.host`` hands out the views of the arena the *next* ``upload_async`` will
+send and first waits (``wait_host_free``) until the DMA that last read that arena has finished.  With two
+slots the host can therefore fill batch i+2 while batch i+1 is still crossing PCIe.
 """
 from __future__ import annotations
 
@@ -60,19 +66,40 @@ class BatchStager:
                 f_off += (n * 4 + 255) // 256 * 256
         self.f32_bytes, self.u8_bytes = f_off, u_off
         self.total = f_off + u_off                          # bytes: [ fp32 entries | 8-bit entries ]
-        self.host_arena = torch.empty(self.total, dtype=torch.uint8).pin_memory()
+        self.host_arenas = [torch.empty(self.total, dtype=torch.uint8).pin_memory() for _ in range(slots)]
         self.dev_arena = [torch.empty(self.total, dtype=torch.uint8, device=self.device) for _ in range(slots)]
         # fp32 expansion of the 8-bit part of each slot
         self.expanded = [torch.empty(max(u_off, 1), dtype=torch.float32, device=self.device) for _ in range(slots)]
-        self.host = {k: self._view(self.host_arena, None, k) for k in self.keys}
+        self._host_views = [{k: self._view(a, None, k) for k in self.keys} for a in self.host_arenas]
         self.ready = [torch.cuda.Event() for _ in range(slots)]
+        self._in_flight = [False] * slots                   # an upload out of host arena s was started and not awaited
         self.consumed = [torch.cuda.Event() for _ in range(slots)]
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.slot = -1
         self._backend = backend
-        for k, v in template.items():
-            if torch.is_tensor(v):
-                self.host[k].copy_(v.detach().cpu())
+        for views in self._host_views:                      # every arena starts out holding the template batch
+            for k, v in template.items():
+                if torch.is_tensor(v):
+                    views[k].copy_(v.detach().cpu())
+
+    @property
+    def next_slot(self):
+        return (self.slot + 1) % len(self.dev_arena)
+
+    def wait_host_free(self, slot=None):
+        """Block the host until the DMA that last read host arena ``slot`` (default: the one the next
+        ``upload_async`` sends) has completed, i.e. until that arena may be rewritten."""
+        s = self.next_slot if slot is None else slot
+        if self._in_flight[s]:
+            self.ready[s].synchronize()
+            self._in_flight[s] = False
+
+    @property
+    def host(self):
+        """Pinned host views (key -> tensor) of the batch the next ``upload_async`` will send.  Safe to
+        write: waits first for the previous upload out of this arena."""
+        self.wait_host_free()
+        return self._host_views[self.next_slot]
 
     def _view(self, arena, expanded, k):
         kind, off, n, shape = self.meta[k]
@@ -92,13 +119,14 @@ class BatchStager:
         s = self.slot
         self.copy_stream.wait_event(self.consumed[s])       # the previous user of this slot is done
         with torch.cuda.stream(self.copy_stream):
-            self.dev_arena[s].copy_(self.host_arena, non_blocking=True)
+            self.dev_arena[s].copy_(self.host_arenas[s], non_blocking=True)
             if self.u8_bytes:
                 from . import _lib
                 be = self._backend if self._backend is not None else _lib.cuda_backend()
                 be.call("u8_to_f32", ctypes.c_void_p(self.dev_arena[s].data_ptr() + self.f32_bytes),
                         ctypes.c_void_p(self.expanded[s].data_ptr()), ctypes.c_size_t(self.u8_bytes))
             self.ready[s].record(self.copy_stream)
+        self._in_flight[s] = True
         return s
 
     def views(self, slot):

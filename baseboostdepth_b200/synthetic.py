@@ -149,4 +149,10 @@ def algorithmic_bytes(plan, height, width, scales):
         reproj += (44 + 24 * d) * hw * len(scales)
         ident += (20 + 12 * d) * hw
     smooth = sum(36 * plan.batch * (height >> s) * (width >> s) for s in scales)
-    return {"reproj": reproj, "identity": ident, "smooth": smooth, "total": reproj + ident + smooth}
+    # the kernels either side of the path: compulsory traffic of the disparity <-> depth steps
+    pyr = sum(plan.batch * (height >> s) * (width >> s) for s in scales)
+    full = plan.batch * hw * len(scales)
+    d2d_fwd = 4 * pyr + 4 * full                 # read every disparity level, write S full-resolution depth planes
+    d2d_bwd = 8 * full + 4 * pyr + 4 * pyr       # read gdepth + depth, read the smoothness gradient, write gdisp
+    return {"reproj": reproj, "identity": ident, "smooth": smooth, "total": reproj + ident + smooth,
+            "d2d_forward": d2d_fwd, "d2d_backward": d2d_bwd}

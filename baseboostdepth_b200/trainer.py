@@ -118,7 +118,7 @@ def loss_step(inputs, outputs, opt, plan: Optional[LossPlan] = None, noise=None,
     # the noise draw and the identity pre-pass below run next to them
     be = backend if backend is not None else _lib.cuda_backend()
     pre = start_side_branch(be, disps, pyramid, (B, H, W), opt.min_depth, opt.max_depth, getattr(opt, "SQL", False),
-                            torch.is_grad_enabled())
+                            torch.is_grad_enabled(), timers=timers)
 
     T = _frame_poses(plan, inputs, outputs, "cam_T_cam", row_masks)
     T_err = _frame_poses(plan, inputs, outputs, "cam_T_cam_error", row_masks) if plan.decomp else None

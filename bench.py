@@ -42,6 +42,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-full-step", action="store_true",
+                    help="skip the full-training-step sub-record (BASELINE.json configs[4])")
+    ap.add_argument("--with-pose", action="store_true",
+                    help="include the pose assembly (axis-angle/translation -> T, SURVEY 8f-2) in the timed step")
     return ap.parse_args()
 
 
@@ -160,7 +164,7 @@ def cpu_reference_run(cfg, steps, warmup, sample_batch=None):
             times.append(dt)
     sec = sum(times) / len(times)
     sample = (f"{c['batch']} of {cfg['batch']} samples of the workload, all scales and sources, "
-              f"{steps} timed steps after {warmup} warm-up")
+              f"{steps} timed steps after {warmup} warm-up, {threads} threads")
     cpu_reference_run.last_probe = {str(k): v for k, v in probe.items()}   # forward-only seconds per thread count
     return pairs / sec, sec, sample, threads
 
@@ -197,14 +201,19 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = workload(args.workload)
-    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 3))
-    value, sec, sample, threads = cpu_reference_run(cfg, steps, warmup, sample_batch=2)
+    # the metric's own configuration: the full batch, all scales and sources, the K / W the caller asked for
+    # (~0.5-3 s per step on the box's host cores depending on the workload)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    value, sec, sample, threads = cpu_reference_run(cfg, steps, warmup, sample_batch=None)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "device": "host CPU",
+            "config": {"workload": args.workload, "batch_per_gpu": cfg["batch"], "height": cfg["height"],
+                       "width": cfg["width"], "scales": 4, "device": "host CPU", "threads": threads,
+                       "host_cores": os.cpu_count(),
+                       "thread_probe_forward_s": getattr(cpu_reference_run, "last_probe", None),
                        "note": "oracle port of the reference's PyTorch loss path (reference is Python; "
-                               "/root/reference cannot travel to the GPU box)"},
+                               "/root/reference cannot travel to the GPU box); full batch, same workload as the GPU arm"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -301,6 +310,22 @@ def run_ours(args):
     launches = be.launches
     step_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
     kern_ms = sum(a.elapsed_time(b) for a, b in kernel_ev if a is not None) / max(1, len(kernel_ev))
+    kernel_name = timers.get("reproj_kernel_name", "bbd::reproj_kernel")
+
+    # ---- per-kernel durations of the rest of the step: the same eager step with every launch of ours bracketed
+    # by CUDA events on its own stream (L2 flushed before each step), mean over a few steps
+    per_call = {}
+    for i in range(min(10, args.steps)):
+        for p in leaves.values():
+            p.grad = None
+        flush.zero_()
+        timers.clear()
+        step()
+        torch.cuda.synchronize()
+        for k, v in timers.items():
+            if isinstance(v, tuple):
+                per_call.setdefault(k, []).append(v[0].elapsed_time(v[1]))
+    per_call = {k: sum(v) / len(v) for k, v in per_call.items()}
 
     # ---- the same step captured once in a CUDA graph and replayed (no Python / launch overhead) ----
     graph_ms = None
@@ -336,7 +361,7 @@ def run_ours(args):
     # Every step uploads its whole batch (images, pyramid, K, stereo_T, disparities, camera motions)
     # from pinned host memory; BatchStager moves it as one DMA on a side stream, double-buffered,
     # so step i+1's upload overlaps step i's kernels.  The loss value is read back every step.
-    e2e_ms, h2d, e2e8_ms, h2d8, e2e_graphed = None, 0, None, 0, False
+    e2e_ms, h2d, e2e8_ms, h2d8, e2e_graphed, h2d_gbs = None, 0, None, 0, False, 0.0
     if not args.no_e2e:
         from baseboostdepth_b200.staging import BatchStager
 
@@ -344,27 +369,39 @@ def run_ours(args):
             return isinstance(k, tuple) and k[0] == "color"
 
         def e2e_measure(frames_8bit):
+            # What a data loader hands over crosses PCIe: the colour frames (and K / inv_K / stereo_T).  The colour
+            # pyramid levels 1..3 are derived on the device from the uploaded frame (mono_dataset.py:187-204 builds
+            # them on the host by resizing), disparities and camera motions are born on the device (network outputs).
             template = {}
             for k, v in inputs.items():
                 if torch.is_tensor(v):
+                    if is_frame(k) and k[2] != 0:
+                        continue                                 # pyramid level: derived on the device
                     if frames_8bit and is_frame(k):
                         v = (v * 255).round().to(torch.uint8)
                     template[("in",) + (k if isinstance(k, tuple) else (k,))] = v
-            template.update({("leaf",) + k: v for k, v in leaves.items() if k[0] in ("disp", "cam_T_cam")})
             stager = BatchStager(template, dev)
+
+            import torch.nn.functional as F
+            dev_leaves = {k: v.detach().clone() for k, v in leaves.items() if k[0] in ("disp", "cam_T_cam")}
 
             def make_io(v):
                 gin = {"ordering": inputs["ordering"]}
                 gout, lv = {}, {}
                 for k, t in v.items():
-                    if k[0] == "in":
-                        gin[k[1] if len(k) == 2 else k[1:]] = t
-                    else:
-                        gout[k[1:]] = lv[k[1:]] = t.detach().requires_grad_(True)
+                    gin[k[1] if len(k) == 2 else k[1:]] = t
+                for k, t in dev_leaves.items():
+                    gout[k] = lv[k] = t.detach().requires_grad_(True)
                 for k in outputs:
                     if k[0] == "cam_T_cam" and k not in gout:
                         gout[k] = outputs[k]
                 return gin, gout, lv
+
+            def derive_pyramid(gin):
+                c0 = gin[("color", 0, 0)]
+                for s_ in (1, 2, 3):
+                    gin[("color", 0, s_)] = F.avg_pool2d(c0, 2 ** s_)
+                return gin
 
             def with_error_poses(gout):
                 if cfg["decomp"]:
@@ -378,13 +415,14 @@ def run_ours(args):
             if not args.no_graph:
                 try:
                     from baseboostdepth_b200.graphed import GraphedLossStep
-                    graphed = GraphedLossStep(stager, make_io, opt, plan, num_scales=4, prepare=with_error_poses)
+                    graphed = GraphedLossStep(stager, make_io, opt, plan, num_scales=4, prepare=with_error_poses,
+                                              prepare_inputs=derive_pyramid)
                 except Exception as exc:  # noqa: BLE001
                     print(f"graphed e2e unavailable: {type(exc).__name__}: {exc}", file=sys.stderr)
 
             def consume(slot):
                 gin, gout, _ = make_io(stager.views(slot))
-                losses = loss_step(gin, with_error_poses(gout), opt, plan, noise=None, num_scales=4)
+                losses = loss_step(derive_pyramid(gin), with_error_poses(gout), opt, plan, noise=None, num_scales=4)
                 losses["loss"].backward()
                 stager.release(slot)
                 return losses["loss"].detach()
@@ -420,6 +458,17 @@ def run_ours(args):
             barrier()
             return sorted(runs)[1], stager.nbytes, graphed is not None
 
+        # host -> device ceiling of this rank while every rank uploads at once (what bounds the fp32 variant)
+        probe_h = torch.empty(128 << 20, dtype=torch.uint8).pin_memory()
+        probe_d = torch.empty(128 << 20, dtype=torch.uint8, device=dev)
+        probe_d.copy_(probe_h, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(8):
+            probe_d.copy_(probe_h, non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_gbs = 8 * probe_h.numel() / (time.perf_counter() - t0) / 1e9
+        del probe_h, probe_d
         e2e_ms, h2d, e2e_graphed = e2e_measure(False)   # fp32 host tensors, as the reference's loader hands them over
         e2e8_ms, h2d8, _ = e2e_measure(True)            # frames kept 8-bit on the host, expanded on the device
 
@@ -431,11 +480,12 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- max over ranks ------------------------------------------------------------------------
-    vals = torch.tensor([step_ms, kern_ms, e2e_ms or 0.0, wall * 1e3 / args.steps, graph_ms or 0.0, e2e8_ms or 0.0],
-                        device=dev, dtype=torch.float64)
+    vals = torch.tensor([step_ms, kern_ms, e2e_ms or 0.0, wall * 1e3 / args.steps, graph_ms or 0.0, e2e8_ms or 0.0,
+                         -h2d_gbs], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    step_ms, kern_ms, e2e_ms_max, wall_ms, graph_ms_max, e2e8_ms_max = (float(v) for v in vals.cpu())
+    step_ms, kern_ms, e2e_ms_max, wall_ms, graph_ms_max, e2e8_ms_max, neg_gbs = (float(v) for v in vals.cpu())
+    h2d_gbs_min = -neg_gbs   # slowest rank's host->device bandwidth with all ranks copying
 
     if rank == 0:
         peaks = {}
@@ -447,10 +497,17 @@ def run_ours(args):
             6650.0, "fallback (B200_PROFILING.md)")
         achieved = abytes["reproj"] / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
         traffic = None
-        try:
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel, one ncu --set full capture
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
         except (OSError, ValueError):
             pass
+        other_bytes = {"ident_forward": abytes["identity"], "smooth_fused": abytes["smooth"],
+                       "disp_to_depth_forward": abytes["d2d_forward"], "disp_to_depth_backward": abytes["d2d_backward"],
+                       "reproj_finalize": None}
+        others = [{"call": "bbd_" + k, "us": per_call[k] * 1e3, "algorithmic_bytes": other_bytes.get(k),
+                   "frac": (other_bytes[k] / (per_call[k] * 1e-3) / 1e9 / peak) if other_bytes.get(k) else None}
+                  for k in ("ident_forward", "smooth_fused", "disp_to_depth_forward", "reproj_finalize",
+                            "disp_to_depth_backward") if k in per_call]
         # headline: the step as the public API runs it in a training loop -- captured once, replayed as a
         # CUDA graph (graphed.GraphedLossStep does the same per staging slot); the eagerly launched step
         # (Python + 14 launches + 3 tensor ops per step) is reported beside it
@@ -469,20 +526,29 @@ def run_ours(args):
                                     else "eager launches"),
                        "eager_ms_per_step": eager_ms, "eager_wall_ms_per_step_incl_flush": wall_ms,
                        "cuda_graph_replay_ms_per_step": graph_ms_max if graph_ms is not None else None},
-            "roofline": {"bound": "hbm", "kernel": "reproj_kernel<true>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": abytes["reproj"],
                          "step_algorithmic_bytes": abytes["total"],
                          "step_frac": abytes["total"] / (step_ms * 1e-3) / 1e9 / peak,
                          "kernel_share_of_eager_step": kern_ms / eager_ms,
-                         "frac_vs_spec_sheet_8000_GBs": (achieved / 8000.0) if achieved else None},
+                         "frac_vs_spec_sheet_8000_GBs": (achieved / 8000.0) if achieved else None,
+                         "others": others,
+                         "others_note": "C-ABI calls of the same step besides the fused kernel, each bracketed by CUDA events "
+                                        "on its own stream in an eager pass (several run concurrently on helper streams, so "
+                                        "their sum exceeds their share of the step); bytes per SURVEY 8(d)"},
             "clocks": clocks, "gpu_launches": launches,
         }
         if e2e_ms is not None:
             line["e2e"] = {"value": pairs * world / (e2e_ms_max * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_max,
                            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                           "how": "loss_step + backward on a batch uploaded from one pinned host arena each step "
+                           "h2d_gbs_per_gpu_all_ranks_copying": h2d_gbs_min,
+                           "h2d_floor_ms_per_step": (h2d / (h2d_gbs_min * 1e9) * 1e3) if h2d_gbs_min > 0 else None,
+                           "uploaded": "what a loader provides: colour frames of every source + K, inv_K, stereo_T; the colour "
+                                       "pyramid levels 1-3 are derived on the device, disparities and camera motions are "
+                                       "device-resident network outputs",
+                           "how": "loss_step + backward on a batch uploaded from a pinned host arena each step "
                                   "(single DMA, double-buffered on a side stream), "
                                   + ("the step replayed as a CUDA graph per staging slot (graphed.GraphedLossStep), every "
                                      "step's loss read back one step behind; " if e2e_graphed else "loss read back each step; ")
@@ -490,11 +556,11 @@ def run_ours(args):
                            "host_affinity": numa,
                            "frames_8bit": {"value": pairs * world / (e2e8_ms_max * 1e-3), "ms_per_step": e2e8_ms_max,
                                            "h2d_bytes_per_step": h2d8,
-                                           "how": "same loop with the colour frames and pyramid staged as the decoder's "
+                                           "how": "same loop with the colour frames staged as the decoder's "
                                                   "8-bit samples and expanded on the device (bbd_u8_to_f32 == ToTensor, "
                                                   "bit-identical) -- the upload is PCIe-bound at N > 1 otherwise"}}
         if not args.no_cpu_baseline and world == 1:
-            v, sec, sample, threads = cpu_reference_run(cfg, steps=2, warmup=1, sample_batch=4)
+            v, sec, sample, threads = cpu_reference_run(cfg, steps=3, warmup=1, sample_batch=None)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                                     "s_per_step": sec,
                                     "thread_probe_forward_s": getattr(cpu_reference_run, "last_probe", None)}
@@ -503,6 +569,19 @@ def run_ours(args):
                 line["cpu_baseline"]["same_code_eager_cuda_ms_per_step"] = eager_cuda_ms(cfg, dev)
             except Exception as exc:  # noqa: BLE001
                 line["cpu_baseline"]["same_code_eager_cuda_ms_per_step"] = f"failed: {type(exc).__name__}"
+    # ---- BASELINE.json configs[4] beside the headline: the full training step on the same N GPUs, with its
+    # NCCL leg (gradient all-reduce of the surrounding networks; the loss path itself has no collective)
+    full = None
+    if not args.no_full_step and args.workload == DEFAULT_WORKLOAD:
+        try:
+            full = full_step_record(args, dev, world, rank, local, cfg["batch"], H, W, steps=min(args.steps, 10),
+                                    context_legs=False)
+        except Exception as exc:  # noqa: BLE001
+            full = {"unavailable": f"{type(exc).__name__}: {exc}"}
+    if rank == 0:
+        if full is not None:
+            line["full_step"] = {k: full[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "e2e", "unavailable")
+                                 if k in full}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -511,56 +590,48 @@ def run_ours(args):
 FULL_STEP = {"full_step_640x192_b12": (12, 192, 640), "full_step_1024x320_b8": (8, 320, 1024)}
 
 
-def run_full_step(args):
-    """BASELINE.json configs[4]: encoder/decoder + pose nets + fused loss + Adam, batch-sharded, NCCL
-    all-reduce of the network gradients (scripts/full_step.py).  Secondary line, not the headline."""
+def full_step_record(args, dev, world, rank, local, B, H, W, steps, context_legs=True):
+    """BASELINE.json configs[4] measured in this process (process group, if any, already initialised):
+    networks + fused loss + Adam, batch-sharded, DDP all-reduce of the network gradients over NCCL.  Returns
+    (record, sampler clocks or None); rank 0's record is meaningful."""
     sys.path.insert(0, os.path.join(ROOT, "scripts"))
     import full_step as FS
     from baseboostdepth_b200 import _lib
-
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    B, H, W = FULL_STEP[args.workload]
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     be = _lib.cuda_backend()
     host = {k: (v.pin_memory() if torch.is_tensor(v) else v)
             for k, v in FS.make_inputs(B, H, W, "cpu", seed=1234 + rank).items()}
     inputs = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def timed(trainer, steps, warmup, upload=False):
-        for _ in range(warmup):
-            trainer.step(inputs)
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        ev0.record()
-        last = None
-        for _ in range(steps):
-            if upload:
-                batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
-                last = float(trainer.step(batch)["loss"])
-            else:
-                last = trainer.step(inputs)["loss"]
-        ev1.record()
-        barrier()
-        wall = (time.perf_counter() - t0) / steps * 1e3
-        ms = ev0.elapsed_time(ev1) / steps
+    def timed(trainer, n, warmup, upload=False, no_sync=False):
+        import contextlib
+        ctx = trainer.ddp.no_sync if (no_sync and trainer.ddp is not None) else contextlib.nullcontext
+        with ctx():
+            for _ in range(warmup):
+                trainer.step(inputs)
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            ev0.record()
+            last = None
+            for _ in range(n):
+                if upload:
+                    batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
+                    last = float(trainer.step(batch)["loss"])
+                else:
+                    last = trainer.step(inputs)["loss"]
+            ev1.record()
+            barrier()
+        wall = (time.perf_counter() - t0) / n * 1e3
+        ms = ev0.elapsed_time(ev1) / n
         t = torch.tensor([ms, wall], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -569,44 +640,70 @@ def run_full_step(args):
     warm = max(3, args.warmup)
     torch.manual_seed(1)
     fused = FS.StepTrainer(B, H, W, dev, loss="fused", ddp=world > 1, local_rank=local)
-    sampler.mark()
     timed(fused, 2, warm)
     be.launches = 0
-    runs = [timed(fused, args.steps, 0) for _ in range(3)]   # eager PyTorch launching ~1,600 kernels per step is
+    runs = [timed(fused, steps, 0) for _ in range(3)]        # eager PyTorch launching ~1,600 kernels per step is
     launches = be.launches // 3                               # jittery: the median of three timed loops is reported
     ms, _, loss = sorted(runs)[1]
-    _, e2e_wall, _ = timed(fused, max(10, min(args.steps, 30)), 2, upload=True)
-    clocks = sampler.stop() if rank == 0 else None
+    nosync_ms = sorted(timed(fused, steps, 1, no_sync=True)[0] for _ in range(3))[1] if world > 1 else None
+    _, e2e_wall, _ = timed(fused, max(10, min(steps, 30)), 2, upload=True)
     legs = {}
-    for name in ("none", "eager"):          # context legs on the same GPU(s), same networks and optimiser
+    for name in (("none", "eager") if context_legs else ("none",)):   # same networks and optimiser, other loss
         torch.manual_seed(1)
         other = FS.StepTrainer(B, H, W, dev, loss=name, ddp=world > 1, local_rank=local)
-        legs[name] = sorted(timed(other, max(5, args.steps // 2), 3 if i == 0 else 0)[0] for i in range(3))[1]
+        legs[name] = sorted(timed(other, max(5, steps // 2), 3 if i == 0 else 0)[0] for i in range(3))[1]
         del other
         torch.cuda.empty_cache()
+    n_params = fused.n_params
+    del fused
+    torch.cuda.empty_cache()
+    rec = {"metric": "training examples/s (full step: networks + fused view-synthesis loss + Adam)",
+           "value": B * world / (ms * 1e-3), "unit": "examples/s", "n_gpus": world, "steps": steps,
+           "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"full_step_{W}x{H}_b{B}", "batch_per_gpu": B, "height": H, "width": W, "scales": 4,
+                      "frames": [0, -1, 1], "network_parameters": n_params,
+                      "networks": "ResNet-18 encoder + skip decoder + 6-channel ResNet-18 pose encoder + pose head, "
+                                  "random init, plain torch/cuDNN fp32 (not the product)",
+                      "sharding": f"batch x{world}; DistributedDataParallel all-reduce of the network gradients "
+                                  f"({n_params * 4 / 1e6:.0f} MB fp32) over NCCL" if world > 1 else "single GPU",
+                      "l2": "working set (activations of a 12-sample ResNet step) far exceeds the 126 MB L2",
+                      "timing": "CUDA events around K steps, max over ranks, median of 3 such loops",
+                      "ms_per_step_all_loops": [r[0] for r in runs],
+                      "ms_per_step_networks_only": legs["none"],
+                      "ms_per_step_without_gradient_allreduce": nosync_ms,
+                      "exposed_allreduce_ms": (ms - nosync_ms) if nosync_ms is not None else None,
+                      "ms_per_step_with_stock_pytorch_loss": legs.get("eager"),
+                      "loss_share_ms_fused": ms - legs["none"],
+                      "loss_share_ms_stock": (legs["eager"] - legs["none"]) if "eager" in legs else None,
+                      "final_loss": loss},
+           "gpu_launches": launches,
+           "e2e": {"value": B * world / (e2e_wall * 1e-3), "unit": "examples/s", "ms_per_step": e2e_wall,
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                   "how": "batch uploaded from pinned host memory every step, loss read back every step; wall clock"}}
+    return rec
+
+
+def run_full_step(args):
+    """BASELINE.json configs[4] as the headline of this invocation (``--workload full_step_...``)."""
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    B, H, W = FULL_STEP[args.workload]
+    sampler = ClockSampler(local)
     if rank == 0:
-        line = {"metric": "training examples/s (full step: networks + fused view-synthesis loss + Adam)",
-                "value": B * world / (ms * 1e-3), "unit": "examples/s", "n_gpus": world, "steps": args.steps,
-                "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": args.workload, "batch_per_gpu": B, "height": H, "width": W, "scales": 4,
-                           "frames": [0, -1, 1], "network_parameters": fused.n_params,
-                           "networks": "ResNet-18 encoder + skip decoder + 6-channel ResNet-18 pose encoder + pose head, "
-                                       "random init, plain torch/cuDNN fp32 (not the product)",
-                           "sharding": f"batch x{world}; DistributedDataParallel all-reduce of the network gradients over NCCL"
-                                       if world > 1 else "single GPU",
-                           "l2": "working set (activations of a 12-sample ResNet step) far exceeds the 126 MB L2",
-                           "timing": "CUDA events around K steps, max over ranks, median of 3 such loops",
-                           "ms_per_step_all_loops": [r[0] for r in runs],
-                           "ms_per_step_networks_only": legs["none"],
-                           "ms_per_step_with_stock_pytorch_loss": legs["eager"],
-                           "loss_share_ms_fused": ms - legs["none"], "loss_share_ms_stock": legs["eager"] - legs["none"],
-                           "final_loss": loss},
-                "clocks": clocks, "gpu_launches": launches,
-                "e2e": {"value": B * world / (e2e_wall * 1e-3), "unit": "examples/s", "ms_per_step": e2e_wall,
-                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                        "how": "batch uploaded from pinned host memory every step, loss read back every step; wall clock"}}
-        emit(line)
+        sampler.start()
+    sampler.mark()
+    rec = full_step_record(args, dev, world, rank, local, B, H, W, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        rec["clocks"] = clocks
+        emit(rec)
     if world > 1:
         dist.destroy_process_group()
 

@@ -127,6 +127,8 @@ int bbd_project_coords(int32_t n, int32_t height, int32_t width, const float* de
 /* (n,3,H,W) planar -> (n,H,W,4) interleaved, 4th component 0: the gather layout of the streaming kernel. */
 int bbd_pack_rgba(int32_t n, int32_t height, int32_t width, const float* planar, float* rgba, bbd_stream_t stream);
 int bbd_reproj_fused(const bbd_reproj_args* a, bbd_stream_t stream);
+/* Symbol (as ncu / nsys print it) of the kernel bbd_reproj_fused launches for these arguments. */
+const char* bbd_reproj_kernel_name(const bbd_reproj_args* a);
 /* loss (S) = sum(loss_part)/(B*H*W); gpose (S,num_pose,3,4) = sum over tiles. */
 int bbd_reproj_finalize(const bbd_reproj_args* a, float* loss, float* gpose, bbd_stream_t stream);
 

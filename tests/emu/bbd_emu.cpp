@@ -200,6 +200,8 @@ int emu_reproj_fused(const bbd_reproj_args* ap) {
   return 0;
 }
 
+const char* emu_reproj_kernel_name(const bbd_reproj_args*) { return "emulation"; }
+
 int emu_reproj_finalize(const bbd_reproj_args* ap, float* loss, float* gpose) {
   const bbd_reproj_args& a = *ap;
   const int ntiles = emu_reproj_tiles(a.height, a.width), used = parts_used(ap);

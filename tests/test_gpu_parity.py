@@ -318,6 +318,24 @@ def test_batch_stager_roundtrip(cuda_device):
     torch.cuda.synchronize()
 
 
+def test_batch_stager_host_rewrite_is_safe(cuda_device):
+    """The host rewrites the pinned views right after starting an upload (what a collate_fn does): no batch
+    may arrive torn.  64 MB per batch, so a DMA is still in flight when the next fill begins; ``stager.host``
+    has to hand out a different pinned arena, and wait for the DMA that last read it."""
+    from baseboostdepth_b200.staging import BatchStager
+    st = BatchStager({"x": torch.zeros(16 << 20)}, cuda_device)
+    seen = []
+    for it in range(7):
+        st.host["x"].fill_(float(it + 1))
+        slot = st.upload_async()
+        v = st.views(slot)["x"]
+        seen.append((v.min(), v.max(), float(it + 1)))
+        st.release(slot)
+    torch.cuda.synchronize()
+    for mn, mx, want in seen:
+        assert float(mn) == want and float(mx) == want, (float(mn), float(mx), want)
+
+
 def test_batch_stager_8bit_frames(cuda_device):
     """8-bit frames cross PCIe as bytes and come out as the fp32 tensors ToTensor would have made
     (datasets/mono_dataset.py:55,201-203: uint8 -> float32 / 255), next to fp32 entries; odd sizes."""
