@@ -2,6 +2,7 @@
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
 // (see baseboostdepth_b200/build.py).  No torch types cross this file's boundary.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 
@@ -208,11 +209,25 @@ __global__ void __launch_bounds__(SCfg::NT, BBD_MIN_BLOCKS) reproj_kernel(const 
 #endif
 template <int K, bool GRAD>
 __global__ void __launch_bounds__(BBD_STREAM_WARPS * 32, BBD_STREAM_MINB) reproj_stream_kernel(const bbd_reproj_args a, int n_units, int part_stride) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x * BBD_STREAM_WARPS + warp;
   if (unit >= n_units) return;  // warp-uniform
-  stream_unit<K, GRAD>(a, unit, lane, smem + (size_t)warp * StreamSmem<K>::FLOATS, part_stride);
+  StreamTmaMaps none = {nullptr, nullptr, nullptr};
+  stream_unit<K, GRAD, false>(a, unit, lane, smem + (size_t)warp * StreamSmem<K, false>::FLOATS, part_stride, none);
+}
+
+// The same kernel with the strip's regular planes (target, depth, identity minimum) staged by the TMA unit.
+template <int K, bool GRAD>
+__global__ void __launch_bounds__(BBD_STREAM_WARPS * 32, BBD_STREAM_MINB)
+    reproj_stream_tma_kernel(const bbd_reproj_args a, int n_units, int part_stride, const __grid_constant__ CUtensorMap tm_tgt,
+                             const __grid_constant__ CUtensorMap tm_dep, const __grid_constant__ CUtensorMap tm_idm) {
+  extern __shared__ __align__(128) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * BBD_STREAM_WARPS + warp;
+  if (unit >= n_units) return;  // warp-uniform
+  StreamTmaMaps maps = {&tm_tgt, &tm_dep, &tm_idm};
+  stream_unit<K, GRAD, true>(a, unit, lane, smem + (size_t)warp * StreamSmem<K, true>::FLOATS, part_stride, maps);
 }
 
 __global__ void stream_coords_kernel(int n, int H, int W, const float* depth, const float* inv_K, const float* P, float* grid,
@@ -622,21 +637,70 @@ static int parts_used(const bbd_reproj_args* a) {
   return use_stream(a) ? StreamGeo::units(a->height, a->width) : tile_parts(a->height, a->width);
 }
 
+#ifndef BBD_STREAM_TMA
+#define BBD_STREAM_TMA (!BBD_STREAM_ASYNC)
+#endif
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    cudaGetLastError();
+  }
+  return fn;
+}
+// (W, H, planes) fp32 tensor, boxes of 36 columns x 1 row x `box_planes`; out-of-range elements read as zero
+static bool make_row_map(CUtensorMap* m, const float* base, int W, int H, long planes, int box_planes) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc || W % 4 != 0 || ((uintptr_t)base & 15) != 0) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+  const cuuint32_t box[3] = {36, 1, (cuuint32_t)box_planes};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int K, bool GRAD>
 static int launch_stream(const bbd_reproj_args* a, cudaStream_t stream) {
+  const int n_units = a->num_scales * a->batch * StreamGeo::units(a->height, a->width);
+  const int blocks = (n_units + BBD_STREAM_WARPS - 1) / BBD_STREAM_WARPS;
+  const int stride = bbd_reproj_tiles(a->height, a->width);
+#if BBD_STREAM_TMA
+  CUtensorMap tt, td, ti;
+  if (make_row_map(&tt, a->target, a->width, a->height, 3L * a->batch, 3) &&
+      make_row_map(&td, a->depth, a->width, a->height, (long)a->num_scales * a->batch, 1) &&
+      make_row_map(&ti, a->ident_min, a->width, a->height, a->batch, 1)) {
+    static bool configured = false;
+    constexpr size_t smem = (size_t)BBD_STREAM_WARPS * StreamSmem<K, true>::FLOATS * sizeof(float);
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(reproj_stream_tma_kernel<K, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return fail((int)e, "reproj_stream_tma_kernel: shared memory attribute");
+      configured = true;
+    }
+    reproj_stream_tma_kernel<K, GRAD><<<blocks, BBD_STREAM_WARPS * 32, smem, stream>>>(*a, n_units, stride, tt, td, ti);
+    return check_launch("reproj_stream_tma_kernel");
+  }
+#endif
+  // widths that are not a multiple of four floats (or unaligned planes) cannot be described to the TMA unit
   static bool configured = false;
-  constexpr size_t smem = (size_t)BBD_STREAM_WARPS * StreamSmem<K>::FLOATS * sizeof(float);
+  constexpr size_t smem = (size_t)BBD_STREAM_WARPS * StreamSmem<K, false>::FLOATS * sizeof(float);
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(reproj_stream_kernel<K, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "reproj_stream_kernel: shared memory attribute");
     configured = true;
   }
-  const int n_units = a->num_scales * a->batch * StreamGeo::units(a->height, a->width);
-  const int blocks = (n_units + BBD_STREAM_WARPS - 1) / BBD_STREAM_WARPS;
-  reproj_stream_kernel<K, GRAD><<<blocks, BBD_STREAM_WARPS * 32, smem, stream>>>(*a, n_units, bbd_reproj_tiles(a->height, a->width));
+  reproj_stream_kernel<K, GRAD><<<blocks, BBD_STREAM_WARPS * 32, smem, stream>>>(*a, n_units, stride);
   return check_launch("reproj_stream_kernel");
 }
-
 
 extern "C" {
 
@@ -703,6 +767,11 @@ int bbd_reproj_fused(const bbd_reproj_args* a, bbd_stream_t stream) {
 const char* bbd_reproj_kernel_name(const bbd_reproj_args* a) {
   if (!a) return "";
   if (use_stream(a)) {
+    const bool tma = BBD_STREAM_TMA && encode_tiled() && a->width % 4 == 0 && !(((uintptr_t)a->target | (uintptr_t)a->depth | (uintptr_t)a->ident_min) & 15);
+    if (tma) {
+      if (a->max_rep == 1) return a->need_grad ? "bbd::reproj_stream_tma_kernel<1, 1>" : "bbd::reproj_stream_tma_kernel<1, 0>";
+      return a->need_grad ? "bbd::reproj_stream_tma_kernel<2, 1>" : "bbd::reproj_stream_tma_kernel<2, 0>";
+    }
     if (a->max_rep == 1) return a->need_grad ? "bbd::reproj_stream_kernel<1, 1>" : "bbd::reproj_stream_kernel<1, 0>";
     return a->need_grad ? "bbd::reproj_stream_kernel<2, 1>" : "bbd::reproj_stream_kernel<2, 0>";
   }

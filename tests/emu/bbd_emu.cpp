@@ -89,9 +89,21 @@ template <int K, bool GRAD>
 static void emu_stream(const bbd_reproj_args& a) {
   const int n_units = a.num_scales * a.batch * StreamGeo::units(a.height, a.width);
   const int stride = emu_reproj_tiles(a.height, a.width);
-  std::vector<float> smem(StreamSmem<K>::FLOATS);
-  for (int unit = 0; unit < n_units; ++unit)
-    simt::run_block(32, [&](int tid) { stream_unit<K, GRAD>(a, unit, tid, smem.data(), stride); });
+  // like the launcher: the TMA-staged variant when the planes can be described to the TMA unit
+  const bool tma = !BBD_STREAM_ASYNC && a.width % 4 == 0;
+  std::vector<float> smem(StreamSmem<K, true>::FLOATS > StreamSmem<K, false>::FLOATS ? StreamSmem<K, true>::FLOATS
+                                                                                      : StreamSmem<K, false>::FLOATS);
+  StreamTmaMaps none = {nullptr, nullptr, nullptr};
+  for (int unit = 0; unit < n_units; ++unit) {
+#if !BBD_STREAM_ASYNC
+    if (tma) {
+      simt::run_block(32, [&](int tid) { stream_unit<K, GRAD, true>(a, unit, tid, smem.data(), stride, none); });
+      continue;
+    }
+#endif
+    simt::run_block(32, [&](int tid) { stream_unit<K, GRAD, false>(a, unit, tid, smem.data(), stride, none); });
+  }
+  (void)tma;
 }
 extern "C" {
 
