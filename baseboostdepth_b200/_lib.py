@@ -37,7 +37,7 @@ class ReprojArgs(C.Structure):
                 ("target", fp), ("frames", fp * MAX_FRAMES), ("depth", fp), ("inv_K", fp), ("P", fp),
                 ("ident_min", fp), ("tab", Tables), ("loss_part", fp), ("gpose_part", fp), ("gdepth", fp),
                 ("winner", fp), ("ident_arg", fp), ("frames_rgba", fp * MAX_FRAMES), ("min_rep", C.c_int32),
-                ("force_tile", C.c_int32)]
+                ("tickets", fp), ("pair_sum", fp), ("loss_out", fp), ("gpose_out", fp), ("force_tile", C.c_int32)]
 
 
 class SmoothArgs(C.Structure):
@@ -64,7 +64,7 @@ EXPORTS = [
     "bbd_backproject_backward", "bbd_project_forward", "bbd_project_chunks", "bbd_project_backward",
     "bbd_ssim_forward", "bbd_ssim_backward", "bbd_pose_pack_forward", "bbd_pose_pack_backward",
     "bbd_pose_forward", "bbd_pose_backward", "bbd_grid_sample_forward", "bbd_grid_sample_backward",
-    "bbd_u8_to_f32", "bbd_loss_combine_forward", "bbd_loss_combine_backward", "bbd_pack_rgba", "bbd_project_coords", "bbd_reproj_kernel_name",
+    "bbd_u8_to_f32", "bbd_loss_combine_forward", "bbd_loss_combine_backward", "bbd_pack_rgba", "bbd_project_coords", "bbd_reproj_kernel_name", "bbd_reproj_finalizes_itself",
 ]
 
 

@@ -735,6 +735,7 @@ int bbd_reproj_fused(const bbd_reproj_args* a, bbd_stream_t stream) {
   if (a->need_grad && (!a->gpose_part || !a->gdepth)) return fail(BBD_E_ARG, "reproj: gradient buffers missing");
   if (a->batch <= 0 || a->height < 2 || a->width < 2 || a->num_scales <= 0) return fail(BBD_E_ARG, "reproj: bad size");
   if (a->max_rep < 1 || a->max_rep > BBD_MAX_REP) return fail(BBD_E_RANGE, "reproj: max_rep out of range");
+  if (a->tickets && !bbd_reproj_finalizes_itself(a)) return fail(BBD_E_ARG, "reproj: tickets given but pair_sum / loss_out / gpose_out missing or tile kernel selected");
   if (use_stream(a)) {
     cudaStream_t st = (cudaStream_t)stream;
     if (a->max_rep == 1) return a->need_grad ? launch_stream<1, true>(a, st) : launch_stream<1, false>(a, st);
@@ -762,6 +763,10 @@ int bbd_reproj_fused(const bbd_reproj_args* a, bbd_stream_t stream) {
   }
   if (rc) return rc;
   return check_launch("reproj_kernel");
+}
+
+int bbd_reproj_finalizes_itself(const bbd_reproj_args* a) {
+  return a && use_stream(a) && a->tickets && a->pair_sum && a->loss_out && (!a->need_grad || a->gpose_out) ? 1 : 0;
 }
 
 const char* bbd_reproj_kernel_name(const bbd_reproj_args* a) {

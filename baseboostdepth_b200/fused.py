@@ -57,6 +57,18 @@ def _call(be, timers, key, name, *args):
     timers[key] = (t0, t1)
 
 
+_TICKETS: Dict = {}
+
+
+def _tickets(device, n):
+    """Zero-initialised int32 counters of the fused finalize; the kernel leaves them zero after every launch."""
+    key = (str(device), n)
+    t = _TICKETS.get(key)
+    if t is None:
+        t = _TICKETS[key] = torch.zeros(n, device=device, dtype=torch.int32)
+    return t
+
+
 def _tables(plan: LossPlan, device):
     cache = getattr(plan, "_dev_tables", None)
     if cache is None or cache[0] != str(device):
@@ -265,16 +277,23 @@ class _FusedLoss(torch.autograd.Function):
         if rgba_arr is not None:
             ra.frames_rgba = rgba_arr
         ra.min_rep, ra.force_tile = min(len(r) for r in plan.rep), int(_FORCE_TILE)
+        # the streaming kernel reduces its own partials (last warp of every (scale, sample), fixed order)
+        reproj = torch.empty(S, **f32)
+        gpose = torch.zeros(S, plan.n_pose, 3, 4, **f32) if need_grad else None
+        fused_finalize = rgba_arr is not None
+        if fused_finalize:
+            ra.tickets = _tickets(dev, S * B + S).data_ptr()
+            pair_sum = torch.empty(S * B, **f32)
+            ra.pair_sum, ra.loss_out, ra.gpose_out = pair_sum.data_ptr(), reproj.data_ptr(), _lib.ptr(gpose)
         timers = cfg.get("timers")
         _call(be, timers, "reproj_fused", "reproj_fused", C.byref(ra))
         if timers is not None and be.cuda:
             timers["reproj_kernel_name"] = be.dll.bbd_reproj_kernel_name(C.byref(ra)).decode()
 
-        # 4. fixed-order reduction of the per-tile partials
-        reproj = torch.empty(S, **f32)
-        gpose = torch.empty(S, plan.n_pose, 3, 4, **f32) if need_grad else None
-        _call(be, timers, "reproj_finalize", "reproj_finalize", C.byref(ra), C.c_void_p(reproj.data_ptr()),
-              C.c_void_p(_lib.ptr(gpose)))
+        # 4. fixed-order reduction of the per-tile partials (tile kernel; the streaming kernel has done it)
+        if not (fused_finalize and be.value("reproj_finalizes_itself", C.byref(ra))):
+            _call(be, timers, "reproj_finalize", "reproj_finalize", C.byref(ra), C.c_void_p(reproj.data_ptr()),
+                  C.c_void_p(_lib.ptr(gpose)))
 
         ctx.cfg = cfg
         ctx.d2d = d2d

@@ -115,6 +115,15 @@ typedef struct bbd_reproj_args {
    * streaming kernel (csrc/bbd_stream.cuh); otherwise the tile kernel, which reads `frames`. */
   const float* frames_rgba[BBD_MAX_FRAMES];
   int32_t min_rep;    /* min n_rep over the batch (0 = unknown: tile kernel) */
+  /* Optional fused finalize (streaming kernel only; see bbd_reproj_finalizes_itself): when `tickets` is set the
+   * last warp of every (scale, sample) reduces that pair's partials in a fixed order and the results land in
+   * loss_out (S) / gpose_out (S,num_pose,3,4) without a second launch.  tickets: S*B + S int32, zero before the
+   * first launch (the kernel leaves them zero); pair_sum: S*B floats of scratch.  gpose_out rows that no
+   * candidate references are not written (zero them once). */
+  int32_t* tickets;
+  float* pair_sum;
+  float* loss_out;
+  float* gpose_out;
   int32_t force_tile; /* != 0: always the tile kernel (exact-rounding arithmetic), for A/B measurements */
 } bbd_reproj_args;
 int bbd_reproj_tiles(int32_t height, int32_t width); /* partial-sum slots per (scale, sample) */
@@ -127,6 +136,9 @@ int bbd_project_coords(int32_t n, int32_t height, int32_t width, const float* de
 /* (n,3,H,W) planar -> (n,H,W,4) interleaved, 4th component 0: the gather layout of the streaming kernel. */
 int bbd_pack_rgba(int32_t n, int32_t height, int32_t width, const float* planar, float* rgba, bbd_stream_t stream);
 int bbd_reproj_fused(const bbd_reproj_args* a, bbd_stream_t stream);
+/* 1 if bbd_reproj_fused, for these arguments, also performs the reduction of bbd_reproj_finalize (tickets given
+ * and the streaming kernel is selected); the caller then skips bbd_reproj_finalize. */
+int bbd_reproj_finalizes_itself(const bbd_reproj_args* a);
 /* Symbol (as ncu / nsys print it) of the kernel bbd_reproj_fused launches for these arguments. */
 const char* bbd_reproj_kernel_name(const bbd_reproj_args* a);
 /* loss (S) = sum(loss_part)/(B*H*W); gpose (S,num_pose,3,4) = sum over tiles. */

@@ -213,6 +213,9 @@ int emu_reproj_fused(const bbd_reproj_args* ap) {
 }
 
 const char* emu_reproj_kernel_name(const bbd_reproj_args*) { return "emulation"; }
+int emu_reproj_finalizes_itself(const bbd_reproj_args* a) {
+  return a && use_stream(a) && a->tickets && a->pair_sum && a->loss_out && (!a->need_grad || a->gpose_out) ? 1 : 0;
+}
 
 int emu_reproj_finalize(const bbd_reproj_args* ap, float* loss, float* gpose) {
   const bbd_reproj_args& a = *ap;
