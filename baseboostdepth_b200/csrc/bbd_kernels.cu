@@ -605,7 +605,10 @@ __global__ void u8_to_f32_tail_kernel(const uint8_t* src, float* dst, size_t beg
 
 // Row-walking kernels: blocks along y per (column block, level).  Thousands of tiny blocks are bound
 // by the block launch rate, not by their work -- a couple of row blocks per SM walk the rows instead.
-constexpr size_t kRowBlocks = 148 * 2;
+#ifndef BBD_ROW_BLOCKS
+#define BBD_ROW_BLOCKS 2
+#endif
+constexpr size_t kRowBlocks = 148 * BBD_ROW_BLOCKS;
 
 static int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;

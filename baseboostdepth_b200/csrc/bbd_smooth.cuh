@@ -67,7 +67,10 @@ BBD_HD float sm_sample_mean(const SmoothArgs& a, int lvl, int b) {
 //     g_disp = g_d * coef[0] - coef[1],   coef = (1/(m+eps), sum(g_d*disp) / (N (m+eps)^2)),
 // which the disparity backward (d2d_backward_px) applies on the fly -- no third pass over the planes.
 // ---------------------------------------------------------------------------------------------------
-constexpr int SMR_TW = 30, SMR_WARPS = 4, SMR_RC = 16;
+#ifndef BBD_SMR_RC
+#define BBD_SMR_RC 16
+#endif
+constexpr int SMR_TW = 30, SMR_WARPS = 4, SMR_RC = BBD_SMR_RC;
 BBD_HD int smr_nbx(int w) { return (w + SMR_TW * SMR_WARPS - 1) / (SMR_TW * SMR_WARPS); }
 BBD_HD int smr_nby(int h) { return (h + SMR_RC - 1) / SMR_RC; }
 BBD_HD int smr_blocks(int h, int w) { return smr_nbx(w) * smr_nby(h); }
