@@ -207,18 +207,18 @@ __global__ void __launch_bounds__(SCfg::NT, BBD_MIN_BLOCKS) reproj_kernel(const 
 #ifndef BBD_STREAM_MINB
 #define BBD_STREAM_MINB 8
 #endif
-template <int K, bool GRAD>
+template <int K, bool GRAD, bool MULTI>
 __global__ void __launch_bounds__(BBD_STREAM_WARPS * 32, BBD_STREAM_MINB) reproj_stream_kernel(const bbd_reproj_args a, int n_units, int part_stride) {
   extern __shared__ __align__(128) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x * BBD_STREAM_WARPS + warp;
   if (unit >= n_units) return;  // warp-uniform
   StreamTmaMaps none = {nullptr, nullptr, nullptr};
-  stream_unit<K, GRAD, false>(a, unit, lane, smem + (size_t)warp * StreamSmem<K, false>::FLOATS, part_stride, none);
+  stream_unit<K, GRAD, false, MULTI>(a, unit, lane, smem + (size_t)warp * StreamSmem<K, false, MULTI>::FLOATS, part_stride, none);
 }
 
 // The same kernel with the strip's regular planes (target, depth, identity minimum) staged by the TMA unit.
-template <int K, bool GRAD>
+template <int K, bool GRAD, bool MULTI>
 __global__ void __launch_bounds__(BBD_STREAM_WARPS * 32, BBD_STREAM_MINB)
     reproj_stream_tma_kernel(const bbd_reproj_args a, int n_units, int part_stride, const __grid_constant__ CUtensorMap tm_tgt,
                              const __grid_constant__ CUtensorMap tm_dep, const __grid_constant__ CUtensorMap tm_idm) {
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(BBD_STREAM_WARPS * 32, BBD_STREAM_MINB)
   const int unit = blockIdx.x * BBD_STREAM_WARPS + warp;
   if (unit >= n_units) return;  // warp-uniform
   StreamTmaMaps maps = {&tm_tgt, &tm_dep, &tm_idm};
-  stream_unit<K, GRAD, true>(a, unit, lane, smem + (size_t)warp * StreamSmem<K, true>::FLOATS, part_stride, maps);
+  stream_unit<K, GRAD, true, MULTI>(a, unit, lane, smem + (size_t)warp * StreamSmem<K, true, MULTI>::FLOATS, part_stride, maps);
 }
 
 __global__ void stream_coords_kernel(int n, int H, int W, const float* depth, const float* inv_K, const float* P, float* grid,
@@ -624,11 +624,14 @@ static int tile_parts(int height, int width) {
   return ((width + SCfg::TW - 1) / SCfg::TW) * ((height + SCfg::TH - 1) / SCfg::TH);
 }
 // slots per (scale, sample) in loss_part / gpose_part: enough for either kernel
-extern "C" int bbd_reproj_tiles(int32_t height, int32_t width) { return std::max(tile_parts(height, width), StreamGeo::units(height, width)); }
+extern "C" int bbd_reproj_tiles(int32_t height, int32_t width) {
+  return std::max(tile_parts(height, width), std::max(StreamGeo::units(height, width), StreamGeoM::units(height, width)));
+}
 
 // Which kernel serves these arguments (the finalize step must agree with the fused launch).
 static bool use_stream(const bbd_reproj_args* a) {
-  if (a->force_tile || a->min_rep < 1 || a->max_rep > 2) return false;
+  if (a->force_tile || a->min_rep < 1 || a->max_rep > BBD_MAX_REP) return false;
+  if (BBD_STREAM_ASYNC && a->max_rep > 2) return false;
   bool any = false;
   for (int f = 0; f < BBD_MAX_FRAMES; ++f) {
     if (a->frames[f] && !a->frames_rgba[f]) return false;
@@ -637,7 +640,8 @@ static bool use_stream(const bbd_reproj_args* a) {
   return any;
 }
 static int parts_used(const bbd_reproj_args* a) {
-  return use_stream(a) ? StreamGeo::units(a->height, a->width) : tile_parts(a->height, a->width);
+  if (!use_stream(a)) return tile_parts(a->height, a->width);
+  return a->max_rep > 2 ? StreamGeoM::units(a->height, a->width) : StreamGeo::units(a->height, a->width);
 }
 
 #ifndef BBD_STREAM_TMA
@@ -672,9 +676,9 @@ static bool make_row_map(CUtensorMap* m, const float* base, int W, int H, long p
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int K, bool GRAD>
+template <int K, bool GRAD, bool MULTI>
 static int launch_stream(const bbd_reproj_args* a, cudaStream_t stream) {
-  const int n_units = a->num_scales * a->batch * StreamGeo::units(a->height, a->width);
+  const int n_units = a->num_scales * a->batch * parts_used(a);
   const int blocks = (n_units + BBD_STREAM_WARPS - 1) / BBD_STREAM_WARPS;
   const int stride = bbd_reproj_tiles(a->height, a->width);
 #if BBD_STREAM_TMA
@@ -683,25 +687,25 @@ static int launch_stream(const bbd_reproj_args* a, cudaStream_t stream) {
       make_row_map(&td, a->depth, a->width, a->height, (long)a->num_scales * a->batch, 1) &&
       make_row_map(&ti, a->ident_min, a->width, a->height, a->batch, 1)) {
     static bool configured = false;
-    constexpr size_t smem = (size_t)BBD_STREAM_WARPS * StreamSmem<K, true>::FLOATS * sizeof(float);
+    constexpr size_t smem = (size_t)BBD_STREAM_WARPS * StreamSmem<K, true, MULTI>::FLOATS * sizeof(float);
     if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(reproj_stream_tma_kernel<K, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = cudaFuncSetAttribute(reproj_stream_tma_kernel<K, GRAD, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return fail((int)e, "reproj_stream_tma_kernel: shared memory attribute");
       configured = true;
     }
-    reproj_stream_tma_kernel<K, GRAD><<<blocks, BBD_STREAM_WARPS * 32, smem, stream>>>(*a, n_units, stride, tt, td, ti);
+    reproj_stream_tma_kernel<K, GRAD, MULTI><<<blocks, BBD_STREAM_WARPS * 32, smem, stream>>>(*a, n_units, stride, tt, td, ti);
     return check_launch("reproj_stream_tma_kernel");
   }
 #endif
   // widths that are not a multiple of four floats (or unaligned planes) cannot be described to the TMA unit
   static bool configured = false;
-  constexpr size_t smem = (size_t)BBD_STREAM_WARPS * StreamSmem<K, false>::FLOATS * sizeof(float);
+  constexpr size_t smem = (size_t)BBD_STREAM_WARPS * StreamSmem<K, false, MULTI>::FLOATS * sizeof(float);
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(reproj_stream_kernel<K, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(reproj_stream_kernel<K, GRAD, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "reproj_stream_kernel: shared memory attribute");
     configured = true;
   }
-  reproj_stream_kernel<K, GRAD><<<blocks, BBD_STREAM_WARPS * 32, smem, stream>>>(*a, n_units, stride);
+  reproj_stream_kernel<K, GRAD, MULTI><<<blocks, BBD_STREAM_WARPS * 32, smem, stream>>>(*a, n_units, stride);
   return check_launch("reproj_stream_kernel");
 }
 
@@ -741,8 +745,11 @@ int bbd_reproj_fused(const bbd_reproj_args* a, bbd_stream_t stream) {
   if (a->tickets && !bbd_reproj_finalizes_itself(a)) return fail(BBD_E_ARG, "reproj: tickets given but pair_sum / loss_out / gpose_out missing or tile kernel selected");
   if (use_stream(a)) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (a->max_rep == 1) return a->need_grad ? launch_stream<1, true>(a, st) : launch_stream<1, false>(a, st);
-    return a->need_grad ? launch_stream<2, true>(a, st) : launch_stream<2, false>(a, st);
+    if (a->max_rep == 1) return a->need_grad ? launch_stream<1, true, false>(a, st) : launch_stream<1, false, false>(a, st);
+    if (a->max_rep == 2) return a->need_grad ? launch_stream<2, true, false>(a, st) : launch_stream<2, false, false>(a, st);
+#if !BBD_STREAM_ASYNC
+    return a->need_grad ? launch_stream<2, true, true>(a, st) : launch_stream<2, false, true>(a, st);
+#endif
   }
   // keep every candidate's warped tile resident while that still allows three blocks per SM
   const bool keep = StripSmem<SCfg>::floats(a->max_rep) * sizeof(float) <= 75 * 1024;
@@ -769,19 +776,17 @@ int bbd_reproj_fused(const bbd_reproj_args* a, bbd_stream_t stream) {
 }
 
 int bbd_reproj_finalizes_itself(const bbd_reproj_args* a) {
-  return a && use_stream(a) && a->tickets && a->pair_sum && a->loss_out && (!a->need_grad || a->gpose_out) ? 1 : 0;
+  return a && use_stream(a) && a->max_rep <= 2 && a->tickets && a->pair_sum && a->loss_out && (!a->need_grad || a->gpose_out) ? 1 : 0;
 }
 
 const char* bbd_reproj_kernel_name(const bbd_reproj_args* a) {
   if (!a) return "";
   if (use_stream(a)) {
     const bool tma = BBD_STREAM_TMA && encode_tiled() && a->width % 4 == 0 && !(((uintptr_t)a->target | (uintptr_t)a->depth | (uintptr_t)a->ident_min) & 15);
-    if (tma) {
-      if (a->max_rep == 1) return a->need_grad ? "bbd::reproj_stream_tma_kernel<1, 1>" : "bbd::reproj_stream_tma_kernel<1, 0>";
-      return a->need_grad ? "bbd::reproj_stream_tma_kernel<2, 1>" : "bbd::reproj_stream_tma_kernel<2, 0>";
-    }
-    if (a->max_rep == 1) return a->need_grad ? "bbd::reproj_stream_kernel<1, 1>" : "bbd::reproj_stream_kernel<1, 0>";
-    return a->need_grad ? "bbd::reproj_stream_kernel<2, 1>" : "bbd::reproj_stream_kernel<2, 0>";
+    static char name[64];
+    snprintf(name, sizeof(name), "bbd::reproj_stream%s_kernel<%d, %d, %d>", tma ? "_tma" : "", a->max_rep == 1 ? 1 : 2, a->need_grad ? 1 : 0,
+             a->max_rep > 2 ? 1 : 0);
+    return name;
   }
   const bool keep = StripSmem<SCfg>::floats(a->max_rep) * sizeof(float) <= 75 * 1024;
   if (a->need_grad) return keep ? "bbd::reproj_kernel<1, 1>" : "bbd::reproj_kernel<1, 0>";

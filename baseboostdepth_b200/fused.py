@@ -97,9 +97,10 @@ def _frame_ptrs(plan: LossPlan, frames: Dict, height, width):
 
 
 def stream_eligible(plan: LossPlan) -> bool:
-    """The streaming kernel handles one or two warped candidates per sample (plain +-m / stereo batches)."""
+    """The streaming kernel serves every batch layout (one or two candidates per sample in one sweep, more in
+    sweeps over candidate pairs); BBD_FORCE_TILE=1 pins the tile kernel."""
     n = [len(r) for r in plan.rep]
-    return (not _FORCE_TILE) and min(n) >= 1 and max(n) <= 2
+    return (not _FORCE_TILE) and min(n) >= 1 and max(n) <= _lib.MAX_REP
 
 
 def rgba_buffers(keep, height, width):
@@ -280,7 +281,7 @@ class _FusedLoss(torch.autograd.Function):
         # the streaming kernel reduces its own partials (last warp of every (scale, sample), fixed order)
         reproj = torch.empty(S, **f32)
         gpose = torch.zeros(S, plan.n_pose, 3, 4, **f32) if need_grad else None
-        fused_finalize = rgba_arr is not None
+        fused_finalize = rgba_arr is not None and plan.max_rep <= 2
         if fused_finalize:
             ra.tickets = _tickets(dev, S * B + S).data_ptr()
             pair_sum = torch.empty(S * B, **f32)

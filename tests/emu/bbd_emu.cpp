@@ -47,12 +47,15 @@ static int tile_parts(int height, int width) {
   return ((width + SCfg::TW - 1) / SCfg::TW) * ((height + SCfg::TH - 1) / SCfg::TH);
 }
 int emu_reproj_tiles(int32_t height, int32_t width) {
-  const int a = tile_parts(height, width), b = StreamGeo::units(height, width);
-  return a > b ? a : b;
+  int a = tile_parts(height, width);
+  if (StreamGeo::units(height, width) > a) a = StreamGeo::units(height, width);
+  if (StreamGeoM::units(height, width) > a) a = StreamGeoM::units(height, width);
+  return a;
 }
 // same choice as the launcher in bbd_kernels.cu
 static bool use_stream(const bbd_reproj_args* a) {
-  if (a->force_tile || a->min_rep < 1 || a->max_rep > 2) return false;
+  if (a->force_tile || a->min_rep < 1 || a->max_rep > BBD_MAX_REP) return false;
+  if (BBD_STREAM_ASYNC && a->max_rep > 2) return false;
   bool any = false;
   for (int f = 0; f < BBD_MAX_FRAMES; ++f) {
     if (a->frames[f] && !a->frames_rgba[f]) return false;
@@ -61,7 +64,8 @@ static bool use_stream(const bbd_reproj_args* a) {
   return any;
 }
 static int parts_used(const bbd_reproj_args* a) {
-  return use_stream(a) ? StreamGeo::units(a->height, a->width) : tile_parts(a->height, a->width);
+  if (!use_stream(a)) return tile_parts(a->height, a->width);
+  return a->max_rep > 2 ? StreamGeoM::units(a->height, a->width) : StreamGeo::units(a->height, a->width);
 }
 
 int emu_project_coords(int32_t n, int32_t H, int32_t W, const float* depth, const float* inv_K, const float* P, float* grid,
@@ -85,23 +89,26 @@ int emu_pack_rgba(int32_t n, int32_t H, int32_t W, const float* planar, float* r
 }
 
 }  // extern "C"
-template <int K, bool GRAD>
+template <int K, bool GRAD, bool MULTI>
 static void emu_stream(const bbd_reproj_args& a) {
-  const int n_units = a.num_scales * a.batch * StreamGeo::units(a.height, a.width);
+  const int n_units = a.num_scales * a.batch * parts_used(&a);
   const int stride = emu_reproj_tiles(a.height, a.width);
   // like the launcher: the TMA-staged variant when the planes can be described to the TMA unit
+#ifdef BBD_EMU_NO_TMA
+  const bool tma = false;
+#else
   const bool tma = !BBD_STREAM_ASYNC && a.width % 4 == 0;
-  std::vector<float> smem(StreamSmem<K, true>::FLOATS > StreamSmem<K, false>::FLOATS ? StreamSmem<K, true>::FLOATS
-                                                                                      : StreamSmem<K, false>::FLOATS);
+#endif
+  std::vector<float> smem(StreamSmem<K, true, MULTI>::FLOATS + StreamSmem<K, false, MULTI>::FLOATS);
   StreamTmaMaps none = {nullptr, nullptr, nullptr};
   for (int unit = 0; unit < n_units; ++unit) {
 #if !BBD_STREAM_ASYNC
     if (tma) {
-      simt::run_block(32, [&](int tid) { stream_unit<K, GRAD, true>(a, unit, tid, smem.data(), stride, none); });
+      simt::run_block(32, [&](int tid) { stream_unit<K, GRAD, true, MULTI>(a, unit, tid, smem.data(), stride, none); });
       continue;
     }
 #endif
-    simt::run_block(32, [&](int tid) { stream_unit<K, GRAD, false>(a, unit, tid, smem.data(), stride, none); });
+    simt::run_block(32, [&](int tid) { stream_unit<K, GRAD, false, MULTI>(a, unit, tid, smem.data(), stride, none); });
   }
   (void)tma;
 }
@@ -144,8 +151,11 @@ int emu_ident_forward(const bbd_ident_args* ap) {
 int emu_reproj_fused(const bbd_reproj_args* ap) {
   const bbd_reproj_args& a = *ap;
   if (use_stream(ap)) {
-    if (a.max_rep == 1) { if (a.need_grad) emu_stream<1, true>(a); else emu_stream<1, false>(a); }
-    else { if (a.need_grad) emu_stream<2, true>(a); else emu_stream<2, false>(a); }
+    if (a.max_rep == 1) { if (a.need_grad) emu_stream<1, true, false>(a); else emu_stream<1, false, false>(a); }
+    else if (a.max_rep == 2) { if (a.need_grad) emu_stream<2, true, false>(a); else emu_stream<2, false, false>(a); }
+#if !BBD_STREAM_ASYNC
+    else { if (a.need_grad) emu_stream<2, true, true>(a); else emu_stream<2, false, true>(a); }
+#endif
     return 0;
   }
   // the CPU harness runs the reuse (non-KEEP) variant for batches with more than two candidates,
@@ -214,7 +224,7 @@ int emu_reproj_fused(const bbd_reproj_args* ap) {
 
 const char* emu_reproj_kernel_name(const bbd_reproj_args*) { return "emulation"; }
 int emu_reproj_finalizes_itself(const bbd_reproj_args* a) {
-  return a && use_stream(a) && a->tickets && a->pair_sum && a->loss_out && (!a->need_grad || a->gpose_out) ? 1 : 0;
+  return a && use_stream(a) && a->max_rep <= 2 && a->tickets && a->pair_sum && a->loss_out && (!a->need_grad || a->gpose_out) ? 1 : 0;
 }
 
 int emu_reproj_finalize(const bbd_reproj_args* ap, float* loss, float* gpose) {
