@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <string.h>
@@ -13,6 +14,7 @@
 #include "bbd_smooth.cuh"
 #include "bbd_strip.cuh"
 #include "bbd_stream.cuh"
+#include "bbd_pipe.cuh"
 
 namespace bbd {
 
@@ -228,6 +230,22 @@ __global__ void __launch_bounds__(BBD_STREAM_WARPS * 32, BBD_STREAM_MINB)
   if (unit >= n_units) return;  // warp-uniform
   StreamTmaMaps maps = {&tm_tgt, &tm_dep, &tm_idm};
   stream_unit<K, GRAD, true, MULTI>(a, unit, lane, smem + (size_t)warp * StreamSmem<K, true, MULTI>::FLOATS, part_stride, maps);
+}
+
+// The pipelined form (bbd_pipe.cuh): one block = one unit, its warps are the gather / statistics / backward
+// stages of the row program.  128 registers per thread -> five blocks (15 warps) per SM.
+#ifndef BBD_PIPE_MINB
+#define BBD_PIPE_MINB 5
+#endif
+template <int K, bool GRAD>
+__global__ void __launch_bounds__(GRAD ? 96 : 64, BBD_PIPE_MINB)
+    reproj_pipe_kernel(const bbd_reproj_args a, int n_units, int part_stride, const __grid_constant__ CUtensorMap tm_tgt,
+                       const __grid_constant__ CUtensorMap tm_dep, const __grid_constant__ CUtensorMap tm_idm) {
+  extern __shared__ __align__(128) float smem[];
+  const int unit = blockIdx.x;
+  if (unit >= n_units) return;  // block-uniform
+  StreamTmaMaps maps = {&tm_tgt, &tm_dep, &tm_idm};
+  pipe_unit<K, GRAD>(a, unit, threadIdx.x, smem, part_stride, maps);
 }
 
 __global__ void stream_coords_kernel(int n, int H, int W, const float* depth, const float* inv_K, const float* P, float* grid,
@@ -676,6 +694,18 @@ static bool make_row_map(CUtensorMap* m, const float* base, int W, int H, long p
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// The pipelined (three-warp) form is an opt-in variant for the single-sweep case (BBD_PIPE=1 in the environment or
+// -DBBD_USE_PIPE=1): parity-green on the B200, but measured slower than the one-warp streaming form (0.453 against
+// 0.418 ms: its three stages are unequal, the gather warp is busy 84 % of the time, the backward warp 53 % --
+// profiles/README.md), so the streaming form stays the default.
+#ifndef BBD_USE_PIPE
+#define BBD_USE_PIPE 0
+#endif
+static bool use_pipe() {
+  const char* e = getenv("BBD_PIPE");  // read per launch: tests switch forms inside one process
+  return e ? (e[0] != '0') : (BBD_USE_PIPE != 0);
+}
+
 template <int K, bool GRAD, bool MULTI>
 static int launch_stream(const bbd_reproj_args* a, cudaStream_t stream) {
   const int n_units = a->num_scales * a->batch * parts_used(a);
@@ -686,6 +716,17 @@ static int launch_stream(const bbd_reproj_args* a, cudaStream_t stream) {
   if (make_row_map(&tt, a->target, a->width, a->height, 3L * a->batch, 3) &&
       make_row_map(&td, a->depth, a->width, a->height, (long)a->num_scales * a->batch, 1) &&
       make_row_map(&ti, a->ident_min, a->width, a->height, a->batch, 1)) {
+    if (!MULTI && use_pipe()) {
+      static bool configured_p = false;
+      constexpr size_t smem_p = (size_t)PipeSmem<K, GRAD>::FLOATS * sizeof(float);
+      if (!configured_p) {
+        cudaError_t e = cudaFuncSetAttribute(reproj_pipe_kernel<K, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
+        if (e != cudaSuccess) return fail((int)e, "reproj_pipe_kernel: shared memory attribute");
+        configured_p = true;
+      }
+      reproj_pipe_kernel<K, GRAD><<<n_units, GRAD ? 96 : 64, smem_p, stream>>>(*a, n_units, stride, tt, td, ti);
+      return check_launch("reproj_pipe_kernel");
+    }
     static bool configured = false;
     constexpr size_t smem = (size_t)BBD_STREAM_WARPS * StreamSmem<K, true, MULTI>::FLOATS * sizeof(float);
     if (!configured) {
@@ -784,8 +825,11 @@ const char* bbd_reproj_kernel_name(const bbd_reproj_args* a) {
   if (use_stream(a)) {
     const bool tma = BBD_STREAM_TMA && encode_tiled() && a->width % 4 == 0 && !(((uintptr_t)a->target | (uintptr_t)a->depth | (uintptr_t)a->ident_min) & 15);
     static char name[64];
-    snprintf(name, sizeof(name), "bbd::reproj_stream%s_kernel<%d, %d, %d>", tma ? "_tma" : "", a->max_rep == 1 ? 1 : 2, a->need_grad ? 1 : 0,
-             a->max_rep > 2 ? 1 : 0);
+    if (tma && a->max_rep <= 2 && use_pipe())
+      snprintf(name, sizeof(name), "bbd::reproj_pipe_kernel<%d, %d>", a->max_rep == 1 ? 1 : 2, a->need_grad ? 1 : 0);
+    else
+      snprintf(name, sizeof(name), "bbd::reproj_stream%s_kernel<%d, %d, %d>", tma ? "_tma" : "", a->max_rep == 1 ? 1 : 2, a->need_grad ? 1 : 0,
+               a->max_rep > 2 ? 1 : 0);
     return name;
   }
   const bool keep = StripSmem<SCfg>::floats(a->max_rep) * sizeof(float) <= 75 * 1024;

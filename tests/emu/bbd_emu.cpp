@@ -18,6 +18,7 @@
 #include "../../baseboostdepth_b200/csrc/bbd_smooth.cuh"
 #include "../../baseboostdepth_b200/csrc/bbd_strip.cuh"
 #include "../../baseboostdepth_b200/csrc/bbd_stream.cuh"
+#include "../../baseboostdepth_b200/csrc/bbd_pipe.cuh"
 
 using namespace bbd;
 #ifndef BBD_TILE_H
@@ -99,10 +100,17 @@ static void emu_stream(const bbd_reproj_args& a) {
 #else
   const bool tma = !BBD_STREAM_ASYNC && a.width % 4 == 0;
 #endif
-  std::vector<float> smem(StreamSmem<K, true, MULTI>::FLOATS + StreamSmem<K, false, MULTI>::FLOATS);
+  std::vector<float> smem(StreamSmem<K, true, MULTI>::FLOATS + StreamSmem<K, false, MULTI>::FLOATS + PipeSmem<K, GRAD>::FLOATS);
   StreamTmaMaps none = {nullptr, nullptr, nullptr};
+  // like the launcher: the pipelined three-warp form for single-sweep launches when BBD_PIPE=1
+  const char* pe = getenv("BBD_PIPE");
+  const bool pipe = tma && !MULTI && (pe ? pe[0] != '0' : false);
   for (int unit = 0; unit < n_units; ++unit) {
 #if !BBD_STREAM_ASYNC
+    if (pipe) {
+      simt::run_block(GRAD ? 96 : 64, [&](int tid) { pipe_unit<K, GRAD>(a, unit, tid, smem.data(), stride, none); });
+      continue;
+    }
     if (tma) {
       simt::run_block(32, [&](int tid) { stream_unit<K, GRAD, true, MULTI>(a, unit, tid, smem.data(), stride, none); });
       continue;

@@ -228,3 +228,29 @@ def test_streaming_kernel_with_short_segments(case):
     for k, v in g.params.items():
         if v.grad is not None:
             assert rel_l2(h.params[k].grad, v.grad) <= 1e-5, k
+
+
+@pytest.mark.parametrize("flags", ["", "-DBBD_STREAM_RH=16 -DBBD_STREAM_RHM=16"])
+def test_pipelined_form(flags, monkeypatch):
+    """The opt-in three-warp form (bbd_pipe.cuh: gather / statistics / backward warps handing rows over through
+    mbarrier-guarded rings) against the oracle, stepped with one fiber per thread of its 96-thread block; with
+    16-row segments the rings wrap and the segment seams are crossed."""
+    monkeypatch.setenv("BBD_PIPE", "1")
+    g = Golden("plain_pm1")
+    ref, aux = O.run(g.inputs, g.outputs, g.opt(), g.noise, num_scales=g.num_scales)
+    ref["loss"].backward()
+    h = Golden("plain_pm1")
+    losses, plan = run_fused(h.inputs, h.outputs, h.opt(), h.noise, h.num_scales, backend=emu_backend(flags), groups=aux["groups"])
+    losses["loss"].backward()
+    for k, v in ref.items():
+        assert abs(float(losses[k]) - float(v)) <= 2e-6 * max(1.0, abs(float(v))), k
+    for k, v in g.params.items():
+        if v.grad is not None:
+            assert rel_l2(h.params[k].grad, v.grad) <= 1e-5, k
+    # and bit-identical to the one-warp streaming form (same arithmetic, same order of adding)
+    monkeypatch.setenv("BBD_PIPE", "0")
+    s = Golden("plain_pm1")
+    losses_s, _ = run_fused(s.inputs, s.outputs, s.opt(), s.noise, s.num_scales, backend=emu_backend(flags), groups=aux["groups"])
+    losses_s["loss"].backward()
+    for k in ref:
+        assert float(losses[k]) == float(losses_s[k]), k

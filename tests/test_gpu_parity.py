@@ -163,6 +163,39 @@ def test_benched_workload_against_oracle(name, cuda_device):
     assert frac_off_outside <= 1e-4, frac_off_outside
 
 
+def test_pipelined_form_on_gpu(cuda_device, monkeypatch):
+    """The opt-in three-warp form of the fused kernel (BBD_PIPE=1, csrc/bbd_pipe.cuh) at the benchmark size: loss and
+    gradients against the one-warp streaming form of the same launch (same arithmetic up to the reciprocal's
+    range handling, same order of adding) and against the oracle."""
+    batch, H, W, baselines, trimin, decomp = WORKLOADS["kitti_640x192_b12_pm1"]
+    scales = [0, 1, 2, 3]
+    opt = O.default_opt(height=H, width=W, trimin=trimin, decomp=decomp, pose_error=5.5, scales=scales, batch_size=batch)
+    cfg = dict(batch=batch, height=H, width=W, baselines=list(baselines), trimin=trimin, decomp=decomp)
+    inputs, outputs, params = make_batch(seed=77, device="cpu", scales=scales, **cfg)
+    plan = plan_for(inputs["ordering"], opt.trimin, opt.decomp, None)
+    noise = make_noise(plan, H, W, seed=78)
+    retain_pose_grads(outputs)
+    ref, aux = O.run(inputs, outputs, opt, noise, num_scales=4)
+    ref["loss"].backward()
+    gnoise = {k: v.to(cuda_device) for k, v in noise.items()}
+    got = {}
+    for form in ("1", "0"):
+        monkeypatch.setenv("BBD_PIPE", form)
+        gi, go, leaves = mirror_to_device(inputs, outputs, params, cuda_device)
+        losses, _ = run_fused(gi, go, opt, gnoise, 4, groups=aux["groups"])
+        losses["loss"].backward()
+        torch.cuda.synchronize()
+        got[form] = (losses, leaves, go["argmin"].clone())
+    lp, gp, wp = got["1"]
+    ls, gs, ws = got["0"]
+    for k in ref:
+        assert abs(float(lp[k]) - float(ref[k])) <= 2e-6 * max(1.0, abs(float(ref[k]))), k
+        assert abs(float(lp[k]) - float(ls[k])) <= 2e-7 * max(1.0, abs(float(ls[k]))), k
+    for k in gp:
+        assert rel_l2(gp[k].grad, gs[k].grad) <= 2e-6, (k, rel_l2(gp[k].grad, gs[k].grad))
+    assert (wp != ws).float().mean().item() <= 1e-5
+
+
 def test_projected_coordinates_bit_exact(cuda_device):
     """north_star clause 1: projected pixel coordinates / tap indices are bit-identical to the reference's.
     Both projection chains of the library -- the tile kernels' (bbd_warp_forward) and the streaming kernel's
