@@ -81,6 +81,21 @@ BBD_HD f2 div_const(const f2& a, float d, float y) {
   return fma_(r, bc2(y), q);
 }
 
+// 16 bytes through the read-only path
+struct f4 {
+  float x, y, z, w;
+};
+BBD_HD f4 load4(const float* p) {
+#if defined(__CUDA_ARCH__)
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  f4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+  return r;
+#else
+  f4 r; r.x = p[0]; r.y = p[1]; r.z = p[2]; r.w = p[3];
+  return r;
+#endif
+}
+
 // SSIM constants (layers.py:232-233), photometric mix (trainer.py:485)
 #define BBD_C1 0.0001f
 #define BBD_C2 0.0009f

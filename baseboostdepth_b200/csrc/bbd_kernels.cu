@@ -487,6 +487,36 @@ __global__ void __launch_bounds__(128) d2d_backward_kernel(const bbd_d2d_args a,
   }
 }
 
+// Single-launch backward: grid (row blocks, levels); a block walks low-resolution rows (b, iy) of its level with a
+// stride of gridDim.x.  Dynamic shared memory = two full-resolution rows of vertical tent sums (double buffer: one
+// barrier per row).
+template <int F>
+__device__ __forceinline__ void d2d_fused_rows(const bbd_d2d_args& a, int lvl, float* sbuf) {
+  const int W = a.width, w = a.w[lvl], h = a.h[lvl];
+  int n = 0;
+  for (int row = blockIdx.x; row < a.batch * h; row += gridDim.x, ++n) {
+    const int b = row / h, iy = row - b * h;
+    float* srow = sbuf + (n & 1) * W;
+    for (int x4 = threadIdx.x * 4; x4 < W; x4 += blockDim.x * 4) {
+      float v[4];
+      d2d_fused_col4<F>(a, lvl, b, iy, x4, v);
+      *reinterpret_cast<float4*>(srow + x4) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __syncthreads();
+    for (int ix = threadIdx.x; ix < w; ix += blockDim.x)
+      a.gdisp[lvl][(size_t)row * w + ix] = d2d_fused_out<F>(a, lvl, b, iy, ix, srow);
+  }
+}
+__global__ void __launch_bounds__(256) d2d_backward_fused_kernel(const bbd_d2d_args a) {
+  extern __shared__ __align__(16) float sbuf[];
+  const int lvl = blockIdx.y;
+  const int f = d2d_fused_factor(a, lvl);
+  if (f == 1) d2d_fused_rows<1>(a, lvl, sbuf);
+  else if (f == 2) d2d_fused_rows<2>(a, lvl, sbuf);
+  else if (f == 4) d2d_fused_rows<4>(a, lvl, sbuf);
+  else d2d_fused_rows<8>(a, lvl, sbuf);
+}
+
 __global__ void pose_kernel(int n, const float* aa, const float* tr, int invert, float* T) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) pose_forward_one(aa + (size_t)i * 3, tr + (size_t)i * 3, invert, T + (size_t)i * 16);
@@ -627,6 +657,9 @@ __global__ void u8_to_f32_tail_kernel(const uint8_t* src, float* dst, size_t beg
 #define BBD_ROW_BLOCKS 2
 #endif
 constexpr size_t kRowBlocks = 148 * BBD_ROW_BLOCKS;
+#ifndef BBD_D2D_ROW_BLOCKS
+#define BBD_D2D_ROW_BLOCKS 3
+#endif
 
 static int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
@@ -944,6 +977,20 @@ int bbd_disp_to_depth_backward_pass2(const bbd_d2d_args* a, int32_t level_begin,
 }
 
 int bbd_disp_to_depth_backward(const bbd_d2d_args* a, bbd_stream_t stream) {
+  if (int rc = d2d_backward_check(a)) return rc;
+  bool fused = (((uintptr_t)a->gdepth | (uintptr_t)a->depth) & 15) == 0 && 2 * (size_t)a->width * sizeof(float) <= 48 * 1024;
+  int max_h = 1;
+  for (int l = 0; l < a->levels; ++l) {
+    fused = fused && d2d_fused_factor(*a, l) != 0;
+    max_h = std::max(max_h, a->h[l]);
+  }
+  if (fused) {  // every level in one launch, no scratch plane
+    const int threads = std::min(256, std::max(32, ((a->width / 4 + 31) / 32) * 32));
+    const size_t rows = (size_t)a->batch * max_h;
+    dim3 grid((unsigned)std::min<size_t>(rows, 148 * BBD_D2D_ROW_BLOCKS), (unsigned)a->levels);
+    d2d_backward_fused_kernel<<<grid, threads, 2 * (size_t)a->width * sizeof(float), (cudaStream_t)stream>>>(*a);
+    return check_launch("d2d_backward_fused_kernel");
+  }
   if (int rc = bbd_disp_to_depth_backward_pass1(a, stream)) return rc;
   return bbd_disp_to_depth_backward_pass2(a, 0, a->levels, stream);
 }

@@ -221,6 +221,85 @@ BBD_HD float d2d_backward_px(const bbd_d2d_args& a, int lvl, int b, int iy, int 
   return acc;
 }
 
+// ---- single-launch backward (integer factors 1, 2, 4, 8; width a multiple of 4) -----------------------------
+// One block owns one low-resolution row (level, sample, iy).  Its threads first walk the 2F full-resolution rows
+// that have iy as a tap, four columns each (16-byte loads of gdepth and depth, chain rule of disp_to_depth applied
+// on the fly), and park the vertical tent sums of the whole row in shared memory; then one thread per
+// low-resolution column adds its 2F neighbours with the horizontal tent weights and finishes the element.
+// No scratch plane, no second launch: every full-resolution element is read by the two blocks whose windows
+// contain it.  The two helpers below are that block's two phases (tests/emu runs them in a plain loop).
+BBD_HD float d2d_epilogue(const bbd_d2d_args& a, int lvl, int b, int iy, int ix, float acc) {
+  const int h = a.h[lvl], w = a.w[lvl];
+  acc *= a.gscale[lvl];
+  if (a.gsmooth[lvl]) {
+    float gs = a.gsmooth[lvl][((size_t)b * h + iy) * w + ix];
+    if (a.gsmooth_coef) {  // finish the deferred mean-normalisation of the smoothness gradient
+      const float* c = a.gsmooth_coef + ((size_t)lvl * a.batch + b) * 2;
+      gs = gs * c[0] - c[1];
+    }
+    acc += a.gsmooth_scale[lvl] * gs;
+  }
+  return acc;
+}
+template <int F>
+BBD_HD void d2d_fused_col4(const bbd_d2d_args& a, int lvl, int b, int iy, int x4, float* v) {
+  const int h = a.h[lvl], H = a.height, W = a.width;
+  const size_t plane = ((size_t)lvl * a.batch + b) * H * W;
+  const float nspan = -a.disp_span;
+  v[0] = v[1] = v[2] = v[3] = 0.0f;
+  constexpr int N = (F == 1) ? 1 : 2 * F;   // rows that have iy as a tap
+  constexpr int CH = N < 8 ? N : 8;         // rows whose loads are issued together (branch-free: a row outside the
+                                            // image is read at a clamped address and weighted 0)
+  const int oy0 = (F == 1) ? iy : iy * F - F / 2;
+#pragma unroll
+  for (int k0 = 0; k0 < N; k0 += CH) {
+    f4 g[CH], d[CH];
+    float wy[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int oy = oy0 + k0 + k;
+      const bool in = oy >= 0 && oy < H;
+      const size_t o = plane + (size_t)(in ? oy : iy * F) * W + x4;
+      wy[k] = in ? ((F == 1) ? 1.0f : d2d_tent<F>(k0 + k - F / 2, iy, h)) : 0.0f;
+      g[k] = load4(a.gdepth + o);
+      if (!a.sql) d[k] = load4(a.depth + o);
+    }
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      float t[4] = {g[k].x, g[k].y, g[k].z, g[k].w};
+      if (!a.sql) {
+        t[0] *= nspan * d[k].x * d[k].x; t[1] *= nspan * d[k].y * d[k].y;
+        t[2] *= nspan * d[k].z * d[k].z; t[3] *= nspan * d[k].w * d[k].w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] += wy[k] * t[j];
+    }
+  }
+}
+template <int F>
+BBD_HD float d2d_fused_out(const bbd_d2d_args& a, int lvl, int b, int iy, int ix, const float* srow) {
+  const int w = a.w[lvl], W = a.width;
+  float acc = 0.0f;
+  if (F == 1) {
+    acc = srow[ix];
+  } else {
+    const int ox0 = ix * F - F / 2;
+#pragma unroll
+    for (int k = 0; k < 2 * F; ++k) {
+      const int ox = ox0 + k;
+      if (ox < 0 || ox >= W) continue;
+      acc += d2d_tent<F>(k - F / 2, ix, w) * srow[ox];
+    }
+  }
+  return d2d_epilogue(a, lvl, b, iy, ix, acc);
+}
+// integer factor of a level for the single-launch path (1, 2, 4, 8), else 0
+BBD_HD int d2d_fused_factor(const bbd_d2d_args& a, int lvl) {
+  if (a.width % 4) return 0;
+  if (a.h[lvl] == a.height && a.w[lvl] == a.width) return 1;
+  return d2d_sep_factor(a, lvl);
+}
+
 // ---- transformation_from_parameters (layers.py:25-100) ---------------------------------------
 // Value with three tangents (d/d axis-angle components); enough operators for the formulas.
 struct Dual3 {

@@ -73,16 +73,6 @@ BBD_HD void mb_wait(float* bar, unsigned parity) {
   (void)bar; (void)parity;
 #endif
 }
-BBD_HD bool elect_one(int lane) {
-#if defined(__CUDA_ARCH__)
-  unsigned pred;
-  asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
-  (void)lane;
-  return pred != 0u;
-#else
-  return lane == 0;
-#endif
-}
 BBD_HD void block_sync() {
 #if defined(__CUDA_ARCH__)
   __syncthreads();
@@ -90,38 +80,6 @@ BBD_HD void block_sync() {
   simt::syncthreads();
 #endif
 }
-
-// ---- V-wide shared-memory access: entry j of a ring row sits at row + (j * 32 + lane) * K floats ----------
-template <class V> BBD_HD V lds_v(const float* p);
-template <> BBD_HD float lds_v<float>(const float* p) { return *p; }
-template <> BBD_HD f2 lds_v<f2>(const float* p) {
-#if defined(__CUDA_ARCH__)
-  const float2 v = *reinterpret_cast<const float2*>(p);
-  return mk2(v.x, v.y);
-#else
-  return mk2(p[0], p[1]);
-#endif
-}
-BBD_HD void sts_v(float* p, float v) { *p = v; }
-BBD_HD void sts_v(float* p, const f2& v) {
-#if defined(__CUDA_ARCH__)
-  *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y);
-#else
-  p[0] = v.x; p[1] = v.y;
-#endif
-}
-// MUFU.RCP without the range scaling of __fdividef (operands here are bounded away from 0 and infinity)
-BBD_HD float rcp_raw(float a) {
-#if defined(__CUDA_ARCH__)
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));
-  return y;
-#else
-  return 1.0f / a;
-#endif
-}
-BBD_HD float vrcp_raw(float a) { return rcp_raw(a); }
-BBD_HD f2 vrcp_raw(const f2& a) { return mk2(rcp_raw(a.x), rcp_raw(a.y)); }
 
 template <int K, bool GRAD>
 struct PipeSmem {

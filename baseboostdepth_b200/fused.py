@@ -28,6 +28,9 @@ import os as _os
 
 # BBD_SIDE_STREAMS=0 keeps every kernel on the launch stream (debugging / A-B measurements)
 _USE_SIDE = _os.environ.get("BBD_SIDE_STREAMS", "1") != "0"
+# 1: the two-pass transpose of the upsample, its full-resolution level on a helper stream (round 1); default: the
+# single-launch form (bbd_disp_to_depth_backward picks it whenever every level is a 1/2/4/8 reduction)
+_SPLIT_D2D_BACKWARD = _os.environ.get("BBD_D2D_SPLIT", "0") != "0"
 # BBD_FORCE_TILE=1 pins the round-1 tile kernel (every elementary operation rounded like the reference's
 # separate ATen kernels) instead of the streaming kernel with contracted / separable arithmetic
 _FORCE_TILE = _os.environ.get("BBD_FORCE_TILE", "0") != "0"
@@ -332,7 +335,7 @@ class _FusedLoss(torch.autograd.Function):
         if timers is not None and be.cuda:
             tb0, tb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             tb0.record()
-        if be.cuda and full_res_first and _USE_SIDE:
+        if be.cuda and full_res_first and _USE_SIDE and _SPLIT_D2D_BACKWARD:
             # pass 2 of a full-resolution level does not read the row sums of pass 1: it runs on a helper
             # stream next to pass 1, the remaining levels follow pass 1 on this stream
             main, (side, _) = torch.cuda.current_stream(), _side_streams(gdepth.device)

@@ -366,7 +366,32 @@ int emu_disp_to_depth_backward_pass2(const bbd_d2d_args* ap, int32_t level_begin
   return 0;
 }
 
+}  // extern "C"
+template <int F>
+static void emu_d2d_fused_level(const bbd_d2d_args& a, int lvl) {
+  std::vector<float> srow(a.width);
+  for (int b = 0; b < a.batch; ++b)
+    for (int iy = 0; iy < a.h[lvl]; ++iy) {
+      for (int x4 = 0; x4 < a.width; x4 += 4) d2d_fused_col4<F>(a, lvl, b, iy, x4, srow.data() + x4);
+      for (int ix = 0; ix < a.w[lvl]; ++ix)
+        a.gdisp[lvl][((size_t)b * a.h[lvl] + iy) * a.w[lvl] + ix] = d2d_fused_out<F>(a, lvl, b, iy, ix, srow.data());
+    }
+}
+extern "C" {
 int emu_disp_to_depth_backward(const bbd_d2d_args* ap) {
+  const bbd_d2d_args& a = *ap;
+  bool fused = true;  // same choice as the launcher
+  for (int l = 0; l < a.levels; ++l) fused = fused && d2d_fused_factor(a, l) != 0;
+  if (fused) {
+    for (int l = 0; l < a.levels; ++l) {
+      const int f = d2d_fused_factor(a, l);
+      if (f == 1) emu_d2d_fused_level<1>(a, l);
+      else if (f == 2) emu_d2d_fused_level<2>(a, l);
+      else if (f == 4) emu_d2d_fused_level<4>(a, l);
+      else emu_d2d_fused_level<8>(a, l);
+    }
+    return 0;
+  }
   emu_disp_to_depth_backward_pass1(ap);
   return emu_disp_to_depth_backward_pass2(ap, 0, ap->levels);
 }

@@ -290,7 +290,9 @@ def test_disp_to_depth_against_autograd(sizes):
     if levels[0] == (H, W):
         parts = backward(True)
         for l in range(S):
-            assert torch.equal(parts[l], whole[l]), l
+            # the single-launch form adds the window column-first, the two passes row-first: same terms, other order
+            assert rel_l2(parts[l], whole[l]) <= 2e-6, l
+            assert rel_l2(parts[l], want_grads[l]) <= 2e-6, l
 
 
 def test_operator_size_sweep():
