@@ -64,6 +64,7 @@ EXPORTS = [
     "bbd_backproject_backward", "bbd_project_forward", "bbd_project_chunks", "bbd_project_backward",
     "bbd_ssim_forward", "bbd_ssim_backward", "bbd_pose_pack_forward", "bbd_pose_pack_backward",
     "bbd_pose_forward", "bbd_pose_backward", "bbd_grid_sample_forward", "bbd_grid_sample_backward",
+    "bbd_grid_sample_dest_keys", "bbd_grid_sample_backward_image",
     "bbd_u8_to_f32", "bbd_loss_combine_forward", "bbd_loss_combine_backward", "bbd_pack_rgba", "bbd_project_coords", "bbd_reproj_kernel_name", "bbd_reproj_finalizes_itself",
 ]
 
@@ -125,7 +126,7 @@ class Backend:
         if self.cuda:
             args = args + (self.stream(),)
         rc = fn(*args)
-        self.launches += {"smooth_fused": 2, "disp_to_depth_backward": 2}.get(name, 1)
+        self.launches += {"smooth_fused": 2, "grid_sample_backward_image": 2}.get(name, 1)
         if rc != 0:
             msg = self.dll.bbd_last_error_string().decode() if self.cuda else ""
             raise RuntimeError(f"bbd_{name} failed with code {rc}: {msg}")

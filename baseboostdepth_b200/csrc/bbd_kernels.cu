@@ -560,6 +560,25 @@ __global__ void grid_sample_grad_kernel(int n, int C, int H, int W, int HoWo, co
     grid_sample_grad_px(C, H, W, HoWo, images, grid, gout, (int)(i / HoWo), (int)(i % HoWo), ggrid);
 }
 
+__global__ void gs_dest_keys_kernel(int n, int H, int W, int HoWo, const float* grid, int32_t* keys) {
+  const size_t total = (size_t)n * HoWo;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    keys[i] = gs_dest_key(H, W, HoWo, grid, (int)(i / HoWo), (int)(i % HoWo));
+}
+__global__ void gs_segment_kernel(const int32_t* keys_sorted, int n_items, int n_keys, int32_t* seg_start) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i <= (size_t)n_items; i += (size_t)gridDim.x * blockDim.x)
+    gs_segment_mark(keys_sorted, n_items, n_keys, (int)i, seg_start);
+}
+__global__ void gs_image_grad_kernel(int n, int C, int H, int W, int HoWo, const float* grid, const float* gout,
+                                     const int32_t* seg_start, const int32_t* order, float* gimg) {
+  const int HW = H * W;
+  const size_t total = (size_t)n * C * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW), c = (int)((i / HW) % C), b = (int)(i / ((size_t)HW * C));
+    gimg[i] = gs_image_grad_px(C, H, W, HoWo, grid, gout, seg_start, order, b, c, p);
+  }
+}
+
 __global__ void backproject_kernel(int n, int H, int W, const float* depth, const float* inv_K, float* points) {
   const int HW = H * W;
   const size_t total = (size_t)n * HW;
@@ -1148,6 +1167,28 @@ int bbd_u8_to_f32(const uint8_t* src, float* dst, size_t n, bbd_stream_t stream)
   if (done < n)
     u8_to_f32_tail_kernel<<<(unsigned)((n - done + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, done, n);
   return check_launch("u8_to_f32_kernel");
+}
+
+int bbd_grid_sample_dest_keys(int32_t n, int32_t height, int32_t width, int32_t out_h, int32_t out_w, const float* grid,
+                              int32_t* keys, bbd_stream_t stream) {
+  if (!grid || !keys) return fail(BBD_E_ARG, "grid_sample keys: null argument");
+  if (n <= 0) return 0;
+  if ((size_t)n * height * width >= (size_t)1 << 31 || (size_t)n * out_h * out_w >= (size_t)1 << 31)
+    return fail(BBD_E_RANGE, "grid_sample keys: more than 2^31 elements");
+  gs_dest_keys_kernel<<<grid_for((size_t)n * out_h * out_w, 256), 256, 0, (cudaStream_t)stream>>>(n, height, width, out_h * out_w, grid, keys);
+  return check_launch("gs_dest_keys_kernel");
+}
+
+int bbd_grid_sample_backward_image(int32_t n, int32_t channels, int32_t height, int32_t width, int32_t out_h, int32_t out_w,
+                                   const float* grid, const float* gout, const int32_t* keys_sorted, const int32_t* order,
+                                   int32_t* seg_start, float* gimages, bbd_stream_t stream) {
+  if (!grid || !gout || !keys_sorted || !order || !seg_start || !gimages) return fail(BBD_E_ARG, "grid_sample image gradient: null argument");
+  if (n <= 0) return 0;
+  const int n_items = n * out_h * out_w, n_keys = n * height * width;
+  gs_segment_kernel<<<grid_for((size_t)n_items + 1, 256), 256, 0, (cudaStream_t)stream>>>(keys_sorted, n_items, n_keys, seg_start);
+  gs_image_grad_kernel<<<grid_for((size_t)n * channels * height * width, 256), 256, 0, (cudaStream_t)stream>>>(
+      n, channels, height, width, out_h * out_w, grid, gout, seg_start, order, gimages);
+  return check_launch("gs_image_grad_kernel");
 }
 
 int bbd_ssim_forward(int32_t n, int32_t channels, int32_t height, int32_t width, const float* x, const float* y, float* out,

@@ -455,6 +455,46 @@ BBD_HD void grid_sample_grad_px(int C, int H, int W, int HoWo, const float* imag
   ggrid[((size_t)n * 2 + 1) * HoWo + o] = giy * s.my * (0.5f * (float)(H - 1));
 }
 
+// ---- gradient w.r.t. the sampled image: the transpose of the bilinear gather, sorted by destination -------
+// ATen scatters every output's upstream gradient onto its four taps with atomic adds (grid_sampler_2d_backward).
+// Here the outputs are sorted by the linear index of their north-west tap (the caller sorts the keys below with a
+// stable sort); a source pixel then finds the outputs that touch it in four contiguous runs of that order (those
+// whose north-west tap is the pixel itself, its west, its north and its north-west neighbour) and adds them in
+// run order -- a gather: no atomics, bit-reproducible.
+BBD_HD int gs_dest_key(int H, int W, int HoWo, const float* grid, int n, int o) {
+  Sample s; Taps t;
+  gs_sample(H, W, grid[((size_t)n * 2) * HoWo + o], grid[((size_t)n * 2 + 1) * HoWo + o], s, t);
+  return n * H * W + t.onw;
+}
+// seg_start[k] = first position of the sorted key array holding a key >= k, for k = 0 .. n_keys (position i marks
+// the keys between its predecessor's and its own)
+BBD_HD void gs_segment_mark(const int32_t* keys_sorted, int n_items, int n_keys, int i, int32_t* seg_start) {
+  const int lo = (i == 0) ? 0 : keys_sorted[i - 1] + 1;
+  const int hi = (i == n_items) ? n_keys : keys_sorted[i];
+  for (int k = lo; k <= hi; ++k) seg_start[k] = i;
+}
+BBD_HD float gs_image_grad_px(int C, int H, int W, int HoWo, const float* grid, const float* gout, const int32_t* seg_start,
+                              const int32_t* order, int n, int c, int p) {
+  const int y = p / W, x = p - y * W;
+  const int base = n * H * W;
+  float acc = 0.0f;
+  // role r: this pixel is the (NW, NE, SW, SE) tap of the outputs whose north-west tap is (p, p-1, p-W, p-W-1)
+  for (int r = 0; r < 4; ++r) {
+    const int dx = r & 1, dy = r >> 1;
+    if ((dx && x == 0) || (dy && y == 0)) continue;
+    const int key = base + p - dx - dy * W;
+    for (int i = seg_start[key]; i < seg_start[key + 1]; ++i) {
+      const int og = order[i];              // global output index n * HoWo + o
+      const int o = og - n * HoWo;
+      Sample s; Taps t;
+      gs_sample(H, W, grid[((size_t)n * 2) * HoWo + o], grid[((size_t)n * 2 + 1) * HoWo + o], s, t);
+      const float w = (r == 0) ? t.wnw : ((r == 1) ? t.wne : ((r == 2) ? t.wsw : t.wse));
+      acc = fma_(gout[((size_t)n * C + c) * HoWo + o], w, acc);
+    }
+  }
+  return acc;
+}
+
 // ---- BackprojectDepth (layers.py:160-167) --------------------------------------------------
 BBD_HD void backproject_px(int HW, int W, const float* depth, const float* inv_K, int n, int i, float* points) {
   const float* ik = inv_K + (size_t)n * 16;

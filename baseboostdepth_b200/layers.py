@@ -252,22 +252,32 @@ class _GridSample(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
-        if ctx.needs_input_grad[0]:
-            raise NotImplementedError("bbd grid_sample: gradient w.r.t. the sampled image is not provided "
-                                      "(the trainer never requests it)")
         be = _backend()
         img, g = ctx.saved_tensors
         n, c, h, w = img.shape
         ho, wo = g.shape[2], g.shape[3]
         go = gout.contiguous()
-        gg = torch.empty_like(g)
-        be.call("grid_sample_backward", n, c, h, w, ho, wo, _p(img), _p(g), _p(go), _p(gg))
-        return None, gg.permute(0, 2, 3, 1)
+        gimg = gg = None
+        if ctx.needs_input_grad[1]:
+            gg = torch.empty_like(g)
+            be.call("grid_sample_backward", n, c, h, w, ho, wo, _p(img), _p(g), _p(go), _p(gg))
+            gg = gg.permute(0, 2, 3, 1)
+        if ctx.needs_input_grad[0]:
+            # transpose of the gather, sorted by destination (no atomics; the trainer itself never asks for it)
+            keys = torch.empty(n * ho * wo, device=img.device, dtype=torch.int32)
+            be.call("grid_sample_dest_keys", n, h, w, ho, wo, _p(g), _p(keys))
+            keys_sorted, order = torch.sort(keys, stable=True)
+            order = order.to(torch.int32)
+            seg = torch.empty(n * h * w + 1, device=img.device, dtype=torch.int32)
+            gimg = torch.empty_like(img)
+            be.call("grid_sample_backward_image", n, c, h, w, ho, wo, _p(g), _p(go), _p(keys_sorted), _p(order), _p(seg), _p(gimg))
+        return gimg, gg
 
 
 def grid_sample(images, grid, align_corners=True, padding_mode="border", mode="bilinear"):
     """``F.grid_sample`` for the one configuration the trainer uses (``trainer.py:439,442``):
-    bilinear, border padding, ``align_corners=True``.  Gradient flows to ``grid`` only.
+    bilinear, border padding, ``align_corners=True``.  Gradients flow to ``grid`` and, when asked for, to
+    ``images`` (a deterministic sorted gather instead of ATen's atomic scatter).
     ``torch.nn.functional.grid_sample = baseboostdepth_b200.layers.grid_sample`` lets an unchanged
     ``trainer.py`` use it (tier A)."""
     if not (align_corners and padding_mode == "border" and mode == "bilinear"):

@@ -252,14 +252,26 @@ int bbd_project_backward(int32_t n, int32_t height, int32_t width, const float* 
                          bbd_stream_t stream);
 /* trainer.py:442 / :439: F.grid_sample(images, grid, align_corners=True, padding_mode="border"),
  * bilinear.  images (n,C,H,W); grid laid out (n,2,Ho,Wo) -- the permuted memory Project3D returns;
- * out (n,C,Ho,Wo).  backward: gradient w.r.t. the grid only (per-pixel gather, deterministic); the
- * source-image gradient (a bilinear splat) is never requested by the trainer and is not provided. */
+ * out (n,C,Ho,Wo).  backward: gradient w.r.t. the grid (per-pixel gather, deterministic); the gradient
+ * w.r.t. the sampled images -- never requested by the trainer -- is the pair of calls further down. */
 int bbd_grid_sample_forward(int32_t n, int32_t channels, int32_t height, int32_t width, int32_t out_h,
                             int32_t out_w, const float* images, const float* grid, float* out,
                             bbd_stream_t stream);
 int bbd_grid_sample_backward(int32_t n, int32_t channels, int32_t height, int32_t width, int32_t out_h,
                              int32_t out_w, const float* images, const float* grid, const float* gout,
                              float* ggrid /* (n,2,Ho,Wo) */, bbd_stream_t stream);
+/* Gradient of F.grid_sample w.r.t. `images` (trainer.py:442 under autograd; ATen grid_sampler_2d_backward scatters it
+ * with atomic adds).  Atomics-free and bit-reproducible: bbd_grid_sample_dest_keys writes, for every output
+ * (n, o) in order, the key n*H*W + (linear index of its north-west tap); the caller sorts the keys with a STABLE
+ * sort (keys_sorted, order = the permutation, as int32); bbd_grid_sample_backward_image then gathers, per source
+ * pixel, the outputs that touch it from four contiguous runs of that order.  seg_start: n*H*W + 1 int32 of
+ * scratch.  gimages (n,C,H,W) is fully written. */
+int bbd_grid_sample_dest_keys(int32_t n, int32_t height, int32_t width, int32_t out_h, int32_t out_w,
+                              const float* grid, int32_t* keys, bbd_stream_t stream);
+int bbd_grid_sample_backward_image(int32_t n, int32_t channels, int32_t height, int32_t width, int32_t out_h,
+                                   int32_t out_w, const float* grid, const float* gout,
+                                   const int32_t* keys_sorted, const int32_t* order, int32_t* seg_start,
+                                   float* gimages, bbd_stream_t stream);
 /* layers.py:235-249; gx / gy may be NULL */
 int bbd_ssim_forward(int32_t n, int32_t channels, int32_t height, int32_t width, const float* x,
                      const float* y, float* out, bbd_stream_t stream);

@@ -455,6 +455,22 @@ int emu_grid_sample_forward(int32_t n, int32_t C, int32_t H, int32_t W, int32_t 
     for (int o = 0; o < Ho * Wo; ++o) grid_sample_px(C, H, W, Ho * Wo, images, grid, b, o, out);
   return 0;
 }
+int emu_grid_sample_dest_keys(int32_t n, int32_t H, int32_t W, int32_t Ho, int32_t Wo, const float* grid, int32_t* keys) {
+  for (int b = 0; b < n; ++b)
+    for (int o = 0; o < Ho * Wo; ++o) keys[(size_t)b * Ho * Wo + o] = gs_dest_key(H, W, Ho * Wo, grid, b, o);
+  return 0;
+}
+int emu_grid_sample_backward_image(int32_t n, int32_t C, int32_t H, int32_t W, int32_t Ho, int32_t Wo, const float* grid,
+                                   const float* gout, const int32_t* keys_sorted, const int32_t* order, int32_t* seg_start,
+                                   float* gimages) {
+  const int n_items = n * Ho * Wo, n_keys = n * H * W;
+  for (int i = 0; i <= n_items; ++i) gs_segment_mark(keys_sorted, n_items, n_keys, i, seg_start);
+  for (int b = 0; b < n; ++b)
+    for (int c = 0; c < C; ++c)
+      for (int p = 0; p < H * W; ++p)
+        gimages[((size_t)b * C + c) * H * W + p] = gs_image_grad_px(C, H, W, Ho * Wo, grid, gout, seg_start, order, b, c, p);
+  return 0;
+}
 int emu_grid_sample_backward(int32_t n, int32_t C, int32_t H, int32_t W, int32_t Ho, int32_t Wo, const float* images,
                              const float* grid, const float* gout, float* ggrid) {
   for (int b = 0; b < n; ++b)

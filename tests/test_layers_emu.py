@@ -216,6 +216,34 @@ def test_grid_sample_matches_aten():
     assert max_abs(res[1][1], res[0][1]) <= 1e-5
 
 
+@pytest.mark.parametrize("shape", [((2, 3, 10, 14), (6, 9)), ((1, 1, 5, 4), (12, 11)), ((3, 2, 8, 8), (8, 8))])
+def test_grid_sample_image_gradient_matches_aten(shape):
+    """d/d(images) of grid_sample (trainer.py:442 under autograd): the sorted gather against ATen's scatter, with
+    coordinates outside the frame (clamped onto the border rows / columns: long runs for one destination),
+    exactly on the border, and more outputs than source pixels."""
+    import torch.nn.functional as F
+    (n, c, h, w), (ho, wo) = shape
+    gen = torch.Generator().manual_seed(5)
+    base = torch.rand(n, 2, ho, wo, generator=gen) * 2.8 - 1.4
+    base[0, 0, 0, 0], base[0, 1, 0, 1] = -1.0, 1.0
+    up = torch.rand(n, c, ho, wo, generator=gen) - 0.3
+    res = []
+    for fn in (lambda i, g: F.grid_sample(i, g, align_corners=True, padding_mode="border"), L.grid_sample):
+        img = torch.rand(n, c, h, w, generator=torch.Generator().manual_seed(6)).requires_grad_(True)
+        raw = base.clone().requires_grad_(True)
+        out = fn(img, raw.permute(0, 2, 3, 1))
+        (out * up).sum().backward()
+        res.append((img.grad.clone(), raw.grad.clone()))
+    assert rel_l2(res[1][0], res[0][0]) <= 1e-6, rel_l2(res[1][0], res[0][0])
+    assert max_abs(res[1][0], res[0][0]) <= 1e-5 * float(res[0][0].abs().max())
+    assert max_abs(res[1][1], res[0][1]) <= 1e-5
+    # the image gradient alone (grid detached), and bit-reproducible
+    img = torch.rand(n, c, h, w, generator=torch.Generator().manual_seed(6)).requires_grad_(True)
+    a = torch.autograd.grad((L.grid_sample(img, base.permute(0, 2, 3, 1)) * up).sum(), img)[0]
+    b = torch.autograd.grad((L.grid_sample(img, base.permute(0, 2, 3, 1)) * up).sum(), img)[0]
+    assert torch.equal(a, b) and torch.equal(a, res[1][0])
+
+
 def test_u8_to_f32_is_totensor():
     """bbd_u8_to_f32 (kernel source stepped on the CPU) == torchvision ToTensor's arithmetic for all 256 codes."""
     import ctypes
