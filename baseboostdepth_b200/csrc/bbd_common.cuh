@@ -31,6 +31,7 @@ BBD_HD float add(float a, float b) { return __fadd_rn(a, b); }
 BBD_HD float sub(float a, float b) { return __fsub_rn(a, b); }
 BBD_HD float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 BBD_HD float div_(float a, float b) { return __fdiv_rn(a, b); }
+BBD_HD float rcp_rn(float a) { return __frcp_rn(a); }  // correctly rounded 1/a (== 1.0f / a, fewer instructions)
 BBD_HD float rcp_approx(float a) { return __fdividef(1.0f, a); }  // gradients only (<= 2 ulp)
 #else
 // host build is compiled with -ffp-contract=off
@@ -39,6 +40,7 @@ BBD_HD float add(float a, float b) { return a + b; }
 BBD_HD float sub(float a, float b) { return a - b; }
 BBD_HD float fma_(float a, float b, float c) { return fmaf(a, b, c); }
 BBD_HD float div_(float a, float b) { return a / b; }
+BBD_HD float rcp_rn(float a) { return 1.0f / a; }
 BBD_HD float rcp_approx(float a) { return 1.0f / a; }
 #endif
 

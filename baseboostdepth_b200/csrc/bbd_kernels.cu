@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(128) d2d_forward_kernel(const bbd_d2d_args a) 
       const int px = g * 4 + k;
       if (px < W) {
         const float up = same ? d[py * W + px] : d2d_up(d, w, ty, tx[k]);
-        v[k] = a.sql ? up : div_(1.0f, add(a.min_disp, mul(a.disp_span, up)));
+        v[k] = a.sql ? up : rcp_rn(add(a.min_disp, mul(a.disp_span, up)));
       } else {
         v[k] = 0.0f;
       }
@@ -487,34 +487,53 @@ __global__ void __launch_bounds__(128) d2d_backward_kernel(const bbd_d2d_args a,
   }
 }
 
-// Single-launch backward: grid (row blocks, levels); a block walks low-resolution rows (b, iy) of its level with a
-// stride of gridDim.x.  Dynamic shared memory = two full-resolution rows of vertical tent sums (double buffer: one
-// barrier per row).
+// Single-launch backward: a persistent grid (all blocks resident) walks the list of low-resolution rows of every
+// level, coarsest level first (a row of the 1/8 level reads sixteen full-resolution rows, one of the full-resolution
+// level a single one), dealt round-robin so that every block gets the same mix.  Dynamic shared memory = two
+// full-resolution rows of vertical tent sums (double buffer: one barrier per row).
+struct D2DRowList {
+  int32_t begin[BBD_MAX_SCALES + 1];  // item range of list position j
+  int32_t level[BBD_MAX_SCALES];      // level at list position j
+};
 template <int F>
-__device__ __forceinline__ void d2d_fused_rows(const bbd_d2d_args& a, int lvl, float* sbuf) {
+__device__ __forceinline__ void d2d_fused_row(const bbd_d2d_args& a, int lvl, int row, float* srow) {
   const int W = a.width, w = a.w[lvl], h = a.h[lvl];
-  int n = 0;
-  for (int row = blockIdx.x; row < a.batch * h; row += gridDim.x, ++n) {
-    const int b = row / h, iy = row - b * h;
-    float* srow = sbuf + (n & 1) * W;
+  const int b = row / h, iy = row - b * h;
+  if (F == 1) {  // same resolution: element-wise, 16 bytes per thread and step
     for (int x4 = threadIdx.x * 4; x4 < W; x4 += blockDim.x * 4) {
       float v[4];
-      d2d_fused_col4<F>(a, lvl, b, iy, x4, v);
-      *reinterpret_cast<float4*>(srow + x4) = make_float4(v[0], v[1], v[2], v[3]);
+      d2d_fused_col4<1>(a, lvl, b, iy, x4, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = d2d_epilogue(a, lvl, b, iy, x4 + j, v[j]);
+      *reinterpret_cast<float4*>(a.gdisp[lvl] + (size_t)row * w + x4) = make_float4(v[0], v[1], v[2], v[3]);
     }
-    __syncthreads();
-    for (int ix = threadIdx.x; ix < w; ix += blockDim.x)
-      a.gdisp[lvl][(size_t)row * w + ix] = d2d_fused_out<F>(a, lvl, b, iy, ix, srow);
+    return;
   }
+  for (int x4 = threadIdx.x * 4; x4 < W; x4 += blockDim.x * 4) {
+    float v[4];
+    d2d_fused_col4<F>(a, lvl, b, iy, x4, v);
+    *reinterpret_cast<float4*>(srow + x4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  __syncthreads();
+  for (int ix = threadIdx.x; ix < w; ix += blockDim.x)
+    a.gdisp[lvl][(size_t)row * w + ix] = d2d_fused_out<F>(a, lvl, b, iy, ix, srow);
 }
-__global__ void __launch_bounds__(256) d2d_backward_fused_kernel(const bbd_d2d_args a) {
+__global__ void __launch_bounds__(256, 3) d2d_backward_fused_kernel(const bbd_d2d_args a, const D2DRowList list) {
   extern __shared__ __align__(16) float sbuf[];
-  const int lvl = blockIdx.y;
-  const int f = d2d_fused_factor(a, lvl);
-  if (f == 1) d2d_fused_rows<1>(a, lvl, sbuf);
-  else if (f == 2) d2d_fused_rows<2>(a, lvl, sbuf);
-  else if (f == 4) d2d_fused_rows<4>(a, lvl, sbuf);
-  else d2d_fused_rows<8>(a, lvl, sbuf);
+  const int total = list.begin[a.levels];
+  int n = 0;
+  for (int i = blockIdx.x; i < total; i += gridDim.x) {
+    int j = 0;
+    while (i >= list.begin[j + 1]) ++j;
+    const int lvl = list.level[j], row = i - list.begin[j];
+    const int f = d2d_fused_factor(a, lvl);
+    float* srow = sbuf + (n & 1) * a.width;
+    if (f == 1) { d2d_fused_row<1>(a, lvl, row, srow); continue; }  // no shared row used: the buffers do not advance
+    if (f == 2) d2d_fused_row<2>(a, lvl, row, srow);
+    else if (f == 4) d2d_fused_row<4>(a, lvl, row, srow);
+    else d2d_fused_row<8>(a, lvl, row, srow);
+    ++n;
+  }
 }
 
 __global__ void pose_kernel(int n, const float* aa, const float* tr, int invert, float* T) {
@@ -1004,10 +1023,28 @@ int bbd_disp_to_depth_backward(const bbd_d2d_args* a, bbd_stream_t stream) {
     max_h = std::max(max_h, a->h[l]);
   }
   if (fused) {  // every level in one launch, no scratch plane
+    D2DRowList list;
+    int order[BBD_MAX_SCALES];
+    for (int l = 0; l < a->levels; ++l) order[l] = l;
+    std::sort(order, order + a->levels, [&](int x, int y) { return a->h[x] < a->h[y]; });  // coarsest (most rows read per row) first
+    list.begin[0] = 0;
+    for (int j = 0; j < a->levels; ++j) {
+      list.level[j] = order[j];
+      list.begin[j + 1] = list.begin[j] + a->batch * a->h[order[j]];
+    }
+    for (int j = a->levels; j < BBD_MAX_SCALES; ++j) { list.level[j] = 0; list.begin[j + 1] = list.begin[a->levels]; }
     const int threads = std::min(256, std::max(32, ((a->width / 4 + 31) / 32) * 32));
-    const size_t rows = (size_t)a->batch * max_h;
-    dim3 grid((unsigned)std::min<size_t>(rows, 148 * BBD_D2D_ROW_BLOCKS), (unsigned)a->levels);
-    d2d_backward_fused_kernel<<<grid, threads, 2 * (size_t)a->width * sizeof(float), (cudaStream_t)stream>>>(*a);
+    static int per_sm = 0;  // resident blocks per SM of this kernel at this block size (queried once)
+    static int per_sm_threads = 0;
+    if (per_sm_threads != threads) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, d2d_backward_fused_kernel, threads, 2 * (size_t)a->width * sizeof(float)) != cudaSuccess || per_sm < 1) per_sm = 1;
+      per_sm_threads = threads;
+    }
+    int sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = std::min(list.begin[a->levels], sms * per_sm);
+    d2d_backward_fused_kernel<<<blocks, threads, 2 * (size_t)a->width * sizeof(float), (cudaStream_t)stream>>>(*a, list);
     return check_launch("d2d_backward_fused_kernel");
   }
   if (int rc = bbd_disp_to_depth_backward_pass1(a, stream)) return rc;

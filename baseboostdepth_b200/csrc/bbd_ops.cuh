@@ -40,7 +40,7 @@ BBD_HD float d2d_forward_px(const bbd_d2d_args& a, int lvl, int b, int oy, int o
   const float* d = a.disp[lvl] + (size_t)b * h * w;
   const float up = d2d_up(d, w, up_taps(oy, h, sy), up_taps(ox, w, sx));
   if (a.sql) return up;
-  return div_(1.0f, add(a.min_disp, mul(a.disp_span, up)));
+  return rcp_rn(add(a.min_disp, mul(a.disp_span, up)));
 }
 
 // one low-resolution disparity pixel: gather d(loss)/d(disp) from the full-res pixels it fed.
@@ -248,11 +248,11 @@ BBD_HD void d2d_fused_col4(const bbd_d2d_args& a, int lvl, int b, int iy, int x4
   const float nspan = -a.disp_span;
   v[0] = v[1] = v[2] = v[3] = 0.0f;
   constexpr int N = (F == 1) ? 1 : 2 * F;   // rows that have iy as a tap
-  constexpr int CH = N < 8 ? N : 8;         // rows whose loads are issued together (branch-free: a row outside the
+  constexpr int CH = N < 4 ? N : 4;         // rows whose loads are issued together (branch-free: a row outside the
                                             // image is read at a clamped address and weighted 0)
   const int oy0 = (F == 1) ? iy : iy * F - F / 2;
-#pragma unroll
-  for (int k0 = 0; k0 < N; k0 += CH) {
+#pragma unroll 1
+  for (int k0 = 0; k0 < N; k0 += CH) {  // kept rolled: one batch of loads in flight at a time, bounded registers
     f4 g[CH], d[CH];
     float wy[CH];
 #pragma unroll
