@@ -515,8 +515,10 @@ __device__ __forceinline__ void d2d_fused_row(const bbd_d2d_args& a, int lvl, in
     *reinterpret_cast<float4*>(srow + x4) = make_float4(v[0], v[1], v[2], v[3]);
   }
   __syncthreads();
-  for (int ix = threadIdx.x; ix < w; ix += blockDim.x)
-    a.gdisp[lvl][(size_t)row * w + ix] = d2d_fused_out<F>(a, lvl, b, iy, ix, srow);
+  for (int base = 0; base < w; base += blockDim.x) {  // block-uniform trip count
+    const int ix = base + threadIdx.x;
+    if (ix < w) a.gdisp[lvl][(size_t)row * w + ix] = d2d_fused_out<F>(a, lvl, b, iy, ix, srow);
+  }
 }
 __global__ void __launch_bounds__(256, 3) d2d_backward_fused_kernel(const bbd_d2d_args a, const D2DRowList list) {
   extern __shared__ __align__(16) float sbuf[];

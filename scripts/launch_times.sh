@@ -8,7 +8,7 @@ rows = list(csv.reader(open(sys.argv[1])))
 h = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
 H = rows[h]; ki, vi = H.index('Kernel Name'), H.index('Metric Value')
 seq = [(r[ki], float(r[vi].replace(',', ''))) for r in rows[h + 1:] if len(r) > vi]
-ends = [i for i, s in enumerate(seq) if 'd2d_backward_kernel' in s[0]]
+ends = [i for i, s in enumerate(seq) if 'd2d_backward' in s[0]]
 starts = [i for i, s in enumerate(seq) if 'd2d_forward_kernel' in s[0]]
 a = max(i for i in starts if i < ends[-1]); b = ends[-1]
 tot = 0
