@@ -210,26 +210,26 @@ __global__ void __launch_bounds__(SCfg::NT, BBD_MIN_BLOCKS) reproj_kernel(const 
 #define BBD_STREAM_MINB 8
 #endif
 template <int K, bool GRAD, bool MULTI>
-__global__ void __launch_bounds__(BBD_STREAM_WARPS * 32, BBD_STREAM_MINB) reproj_stream_kernel(const bbd_reproj_args a, int n_units, int part_stride) {
+__global__ void __launch_bounds__(BBD_STREAM_WARPS * 32, BBD_STREAM_MINB) reproj_stream_kernel(const bbd_reproj_args a, int n_units, int part_stride, int seg_rows) {
   extern __shared__ __align__(128) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x * BBD_STREAM_WARPS + warp;
   if (unit >= n_units) return;  // warp-uniform
   StreamTmaMaps none = {nullptr, nullptr, nullptr};
-  stream_unit<K, GRAD, false, MULTI>(a, unit, lane, smem + (size_t)warp * StreamSmem<K, false, MULTI>::FLOATS, part_stride, none);
+  stream_unit<K, GRAD, false, MULTI>(a, unit, lane, smem + (size_t)warp * StreamSmem<K, false, MULTI>::FLOATS, part_stride, none, seg_rows);
 }
 
 // The same kernel with the strip's regular planes (target, depth, identity minimum) staged by the TMA unit.
 template <int K, bool GRAD, bool MULTI>
 __global__ void __launch_bounds__(BBD_STREAM_WARPS * 32, BBD_STREAM_MINB)
     reproj_stream_tma_kernel(const bbd_reproj_args a, int n_units, int part_stride, const __grid_constant__ CUtensorMap tm_tgt,
-                             const __grid_constant__ CUtensorMap tm_dep, const __grid_constant__ CUtensorMap tm_idm) {
+                             const __grid_constant__ CUtensorMap tm_dep, const __grid_constant__ CUtensorMap tm_idm, int seg_rows) {
   extern __shared__ __align__(128) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x * BBD_STREAM_WARPS + warp;
   if (unit >= n_units) return;  // warp-uniform
   StreamTmaMaps maps = {&tm_tgt, &tm_dep, &tm_idm};
-  stream_unit<K, GRAD, true, MULTI>(a, unit, lane, smem + (size_t)warp * StreamSmem<K, true, MULTI>::FLOATS, part_stride, maps);
+  stream_unit<K, GRAD, true, MULTI>(a, unit, lane, smem + (size_t)warp * StreamSmem<K, true, MULTI>::FLOATS, part_stride, maps, seg_rows);
 }
 
 // The pipelined form (bbd_pipe.cuh): one block = one unit, its warps are the gather / statistics / backward
@@ -240,12 +240,12 @@ __global__ void __launch_bounds__(BBD_STREAM_WARPS * 32, BBD_STREAM_MINB)
 template <int K, bool GRAD>
 __global__ void __launch_bounds__(GRAD ? 96 : 64, BBD_PIPE_MINB)
     reproj_pipe_kernel(const bbd_reproj_args a, int n_units, int part_stride, const __grid_constant__ CUtensorMap tm_tgt,
-                       const __grid_constant__ CUtensorMap tm_dep, const __grid_constant__ CUtensorMap tm_idm) {
+                       const __grid_constant__ CUtensorMap tm_dep, const __grid_constant__ CUtensorMap tm_idm, int seg_rows) {
   extern __shared__ __align__(128) float smem[];
   const int unit = blockIdx.x;
   if (unit >= n_units) return;  // block-uniform
   StreamTmaMaps maps = {&tm_tgt, &tm_dep, &tm_idm};
-  pipe_unit<K, GRAD>(a, unit, threadIdx.x, smem, part_stride, maps);
+  pipe_unit<K, GRAD>(a, unit, threadIdx.x, smem, part_stride, maps, seg_rows);
 }
 
 __global__ void stream_coords_kernel(int n, int H, int W, const float* depth, const float* inv_K, const float* P, float* grid,
@@ -259,10 +259,10 @@ __global__ void stream_coords_kernel(int n, int H, int W, const float* depth, co
 struct RgbaPtrs {
   float* p[BBD_MAX_FRAMES];
 };
-__global__ void __launch_bounds__(32) ident_stream_kernel(const bbd_ident_args a, const RgbaPtrs rgba, int n_units) {
+__global__ void __launch_bounds__(32) ident_stream_kernel(const bbd_ident_args a, const RgbaPtrs rgba, int n_units, int seg_rows) {
   const int unit = blockIdx.x;
   if (unit >= n_units) return;
-  ident_unit(a, rgba.p, unit, threadIdx.x);
+  ident_unit(a, rgba.p, unit, threadIdx.x, seg_rows);
 }
 
 // (n,3,H,W) -> (n,H,W,4): a thread converts four consecutive pixels (3 x 16 B in, 4 x 16 B out)
@@ -716,7 +716,7 @@ static int tile_parts(int height, int width) {
 }
 // slots per (scale, sample) in loss_part / gpose_part: enough for either kernel
 extern "C" int bbd_reproj_tiles(int32_t height, int32_t width) {
-  return std::max(tile_parts(height, width), std::max(StreamGeo::units(height, width), StreamGeoM::units(height, width)));
+  return std::max(tile_parts(height, width), std::max(StreamGeo::strips(width) * stream_max_segs(height), StreamGeoM::units(height, width)));
 }
 
 // Which kernel serves these arguments (the finalize step must agree with the fused launch).
@@ -730,9 +730,24 @@ static bool use_stream(const bbd_reproj_args* a) {
   }
   return any;
 }
+// resident warps of the one-warp streaming form on this device (8 per SM: 224-243 registers per thread)
+static int stream_slots() {
+  static int slots = 0;
+  if (!slots) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    slots = sms * BBD_STREAM_MINB;
+  }
+  return slots;
+}
+static int seg_rows_for(const bbd_reproj_args* a) {
+  return stream_seg_rows(a->height, a->width, a->num_scales * a->batch, stream_slots());
+}
 static int parts_used(const bbd_reproj_args* a) {
   if (!use_stream(a)) return tile_parts(a->height, a->width);
-  return a->max_rep > 2 ? StreamGeoM::units(a->height, a->width) : StreamGeo::units(a->height, a->width);
+  if (a->max_rep > 2) return StreamGeoM::units(a->height, a->width);
+  const int rh = seg_rows_for(a);
+  return StreamGeo::strips(a->width) * ((a->height + rh - 1) / rh);
 }
 
 #ifndef BBD_STREAM_TMA
@@ -783,6 +798,7 @@ template <int K, bool GRAD, bool MULTI>
 static int launch_stream(const bbd_reproj_args* a, cudaStream_t stream) {
   const int n_units = a->num_scales * a->batch * parts_used(a);
   const int blocks = (n_units + BBD_STREAM_WARPS - 1) / BBD_STREAM_WARPS;
+  const int seg_rows = MULTI ? BBD_STREAM_RHM : seg_rows_for(a);
   const int stride = bbd_reproj_tiles(a->height, a->width);
 #if BBD_STREAM_TMA
   CUtensorMap tt, td, ti;
@@ -797,7 +813,7 @@ static int launch_stream(const bbd_reproj_args* a, cudaStream_t stream) {
         if (e != cudaSuccess) return fail((int)e, "reproj_pipe_kernel: shared memory attribute");
         configured_p = true;
       }
-      reproj_pipe_kernel<K, GRAD><<<n_units, GRAD ? 96 : 64, smem_p, stream>>>(*a, n_units, stride, tt, td, ti);
+      reproj_pipe_kernel<K, GRAD><<<n_units, GRAD ? 96 : 64, smem_p, stream>>>(*a, n_units, stride, tt, td, ti, seg_rows);
       return check_launch("reproj_pipe_kernel");
     }
     static bool configured = false;
@@ -807,7 +823,7 @@ static int launch_stream(const bbd_reproj_args* a, cudaStream_t stream) {
       if (e != cudaSuccess) return fail((int)e, "reproj_stream_tma_kernel: shared memory attribute");
       configured = true;
     }
-    reproj_stream_tma_kernel<K, GRAD, MULTI><<<blocks, BBD_STREAM_WARPS * 32, smem, stream>>>(*a, n_units, stride, tt, td, ti);
+    reproj_stream_tma_kernel<K, GRAD, MULTI><<<blocks, BBD_STREAM_WARPS * 32, smem, stream>>>(*a, n_units, stride, tt, td, ti, seg_rows);
     return check_launch("reproj_stream_tma_kernel");
   }
 #endif
@@ -819,7 +835,7 @@ static int launch_stream(const bbd_reproj_args* a, cudaStream_t stream) {
     if (e != cudaSuccess) return fail((int)e, "reproj_stream_kernel: shared memory attribute");
     configured = true;
   }
-  reproj_stream_kernel<K, GRAD, MULTI><<<blocks, BBD_STREAM_WARPS * 32, smem, stream>>>(*a, n_units, stride);
+  reproj_stream_kernel<K, GRAD, MULTI><<<blocks, BBD_STREAM_WARPS * 32, smem, stream>>>(*a, n_units, stride, seg_rows);
   return check_launch("reproj_stream_kernel");
 }
 
@@ -834,8 +850,11 @@ int bbd_ident_forward(const bbd_ident_args* a, bbd_stream_t stream) {
   if (!a->force_tile) {
     RgbaPtrs rp;
     for (int f = 0; f < BBD_MAX_FRAMES; ++f) rp.p[f] = a->frames_rgba[f];
-    const int n_units = a->batch * IdentGeo::units(a->height, a->width);
-    ident_stream_kernel<<<n_units, 32, 0, (cudaStream_t)stream>>>(*a, rp, n_units);
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int seg_rows = ident_seg_rows(a->height, a->width, a->batch, sms * 16);
+    const int n_units = a->batch * IdentGeo::strips(a->width) * ((a->height + seg_rows - 1) / seg_rows);
+    ident_stream_kernel<<<n_units, 32, 0, (cudaStream_t)stream>>>(*a, rp, n_units, seg_rows);
     return check_launch("ident_stream_kernel");
   }
   dim3 grid((a->width + SCfg::TW - 1) / SCfg::TW, (a->height + SCfg::TH - 1) / SCfg::TH, a->batch);

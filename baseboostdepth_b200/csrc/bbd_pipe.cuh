@@ -107,11 +107,11 @@ struct PipeCtx {
   int s, b, sb, x0, y0, y1, u, px, n_rows, unit_in_sb, upb, n_rep_raw;
   bool col_in, centre_lane, own_lane;
 };
-BBD_HD PipeCtx pipe_ctx(const bbd_reproj_args& a, int unit, int lane) {
+BBD_HD PipeCtx pipe_ctx(const bbd_reproj_args& a, int unit, int lane, int seg_rows) {
   typedef StreamGeo Geo;
   PipeCtx c;
   const int H = a.height, W = a.width;
-  const int nstrips = Geo::strips(W), nsegs = Geo::segs(H);
+  const int nstrips = Geo::strips(W), nsegs = (H + seg_rows - 1) / seg_rows;
   c.upb = nstrips * nsegs;
   c.s = unit % a.num_scales;  // scale-minor unit order, as stream_unit
   const int rest = unit / a.num_scales;
@@ -121,8 +121,8 @@ BBD_HD PipeCtx pipe_ctx(const bbd_reproj_args& a, int unit, int lane) {
   const int seg = rem / nstrips, strip = rem - seg * nstrips;
   c.unit_in_sb = rem;
   c.x0 = strip * Geo::TW;
-  c.y0 = seg * Geo::RH;
-  c.y1 = (c.y0 + Geo::RH < H) ? c.y0 + Geo::RH : H;
+  c.y0 = seg * seg_rows;
+  c.y1 = (c.y0 + seg_rows < H) ? c.y0 + seg_rows : H;
   c.n_rows = c.y1 - c.y0 + 4;  // rows y0-2 .. y1+1
   c.u = c.x0 - 2 + lane;
   c.px = reflect1(c.u, W);
@@ -626,7 +626,7 @@ BBD_HD void pipe_finalize(const bbd_reproj_args& a, const PipeCtx& c, int lane, 
 
 // One block of (GRAD ? 3 : 2) warps = one unit.  `tid` is the thread index in the block.
 template <int K, bool GRAD>
-BBD_HD void pipe_unit(const bbd_reproj_args& a, int unit, int tid, float* smem, int part_stride, const StreamTmaMaps& tm) {
+BBD_HD void pipe_unit(const bbd_reproj_args& a, int unit, int tid, float* smem, int part_stride, const StreamTmaMaps& tm, int seg_rows) {
   typedef PipeSmem<K, GRAD> SM;
   const int warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -635,7 +635,7 @@ BBD_HD void pipe_unit(const bbd_reproj_args& a, int unit, int tid, float* smem, 
     mb_init_fence();
   }
   block_sync();
-  const PipeCtx c = pipe_ctx(a, unit, lane);
+  const PipeCtx c = pipe_ctx(a, unit, lane, seg_rows);
   if (warp == 0) {
     pipe_gather<K, GRAD>(a, c, lane, smem, tm);
   } else if (warp == 1) {

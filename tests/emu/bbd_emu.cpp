@@ -49,7 +49,7 @@ static int tile_parts(int height, int width) {
 }
 int emu_reproj_tiles(int32_t height, int32_t width) {
   int a = tile_parts(height, width);
-  if (StreamGeo::units(height, width) > a) a = StreamGeo::units(height, width);
+  if (StreamGeo::strips(width) * stream_max_segs(height) > a) a = StreamGeo::strips(width) * stream_max_segs(height);
   if (StreamGeoM::units(height, width) > a) a = StreamGeoM::units(height, width);
   return a;
 }
@@ -66,7 +66,9 @@ static bool use_stream(const bbd_reproj_args* a) {
 }
 static int parts_used(const bbd_reproj_args* a) {
   if (!use_stream(a)) return tile_parts(a->height, a->width);
-  return a->max_rep > 2 ? StreamGeoM::units(a->height, a->width) : StreamGeo::units(a->height, a->width);
+  if (a->max_rep > 2) return StreamGeoM::units(a->height, a->width);
+  const int rh = stream_seg_rows(a->height, a->width, a->num_scales * a->batch, 148 * 8);
+  return StreamGeo::strips(a->width) * ((a->height + rh - 1) / rh);
 }
 
 int emu_project_coords(int32_t n, int32_t H, int32_t W, const float* depth, const float* inv_K, const float* P, float* grid,
@@ -102,21 +104,22 @@ static void emu_stream(const bbd_reproj_args& a) {
 #endif
   std::vector<float> smem(StreamSmem<K, true, MULTI>::FLOATS + StreamSmem<K, false, MULTI>::FLOATS + PipeSmem<K, GRAD>::FLOATS);
   StreamTmaMaps none = {nullptr, nullptr, nullptr};
+  const int seg_rows = MULTI ? BBD_STREAM_RHM : stream_seg_rows(a.height, a.width, a.num_scales * a.batch, 148 * 8);
   // like the launcher: the pipelined three-warp form for single-sweep launches when BBD_PIPE=1
   const char* pe = getenv("BBD_PIPE");
   const bool pipe = tma && !MULTI && (pe ? pe[0] != '0' : false);
   for (int unit = 0; unit < n_units; ++unit) {
 #if !BBD_STREAM_ASYNC
     if (pipe) {
-      simt::run_block(GRAD ? 96 : 64, [&](int tid) { pipe_unit<K, GRAD>(a, unit, tid, smem.data(), stride, none); });
+      simt::run_block(GRAD ? 96 : 64, [&](int tid) { pipe_unit<K, GRAD>(a, unit, tid, smem.data(), stride, none, seg_rows); });
       continue;
     }
     if (tma) {
-      simt::run_block(32, [&](int tid) { stream_unit<K, GRAD, true, MULTI>(a, unit, tid, smem.data(), stride, none); });
+      simt::run_block(32, [&](int tid) { stream_unit<K, GRAD, true, MULTI>(a, unit, tid, smem.data(), stride, none, seg_rows); });
       continue;
     }
 #endif
-    simt::run_block(32, [&](int tid) { stream_unit<K, GRAD, false, MULTI>(a, unit, tid, smem.data(), stride, none); });
+    simt::run_block(32, [&](int tid) { stream_unit<K, GRAD, false, MULTI>(a, unit, tid, smem.data(), stride, none, seg_rows); });
   }
   (void)tma;
 }
@@ -125,9 +128,10 @@ extern "C" {
 int emu_ident_forward(const bbd_ident_args* ap) {
   const bbd_ident_args& a = *ap;
   if (!a.force_tile) {
-    const int n_units = a.batch * IdentGeo::units(a.height, a.width);
+    const int seg_rows = ident_seg_rows(a.height, a.width, a.batch, 148 * 16);
+    const int n_units = a.batch * IdentGeo::strips(a.width) * ((a.height + seg_rows - 1) / seg_rows);
     for (int unit = 0; unit < n_units; ++unit)
-      simt::run_block(32, [&](int tid) { ident_unit(a, const_cast<float* const*>(a.frames_rgba), unit, tid); });
+      simt::run_block(32, [&](int tid) { ident_unit(a, const_cast<float* const*>(a.frames_rgba), unit, tid, seg_rows); });
     return 0;
   }
   std::vector<float> smem(IdentStripSmem<SCfg>::floats());
