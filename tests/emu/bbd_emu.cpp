@@ -78,6 +78,8 @@ int emu_project_coords(int32_t n, int32_t H, int32_t W, const float* depth, cons
   return 0;
 }
 
+long emu_skipped_sweeps_total(void) { return emu_skipped_sweeps(); }
+
 int emu_pack_rgba(int32_t n, int32_t H, int32_t W, const float* planar, float* rgba) {
   const size_t HW = (size_t)H * W;
   for (size_t img = 0; img < (size_t)n; ++img)

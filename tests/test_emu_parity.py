@@ -254,3 +254,35 @@ def test_pipelined_form(flags, monkeypatch):
     losses_s["loss"].backward()
     for k in ref:
         assert float(losses[k]) == float(losses_s[k]), k
+
+
+def test_far_baselines_that_never_win():
+    """Tri-min batch whose +-2 / +-3 frames are far from the target (inverted intensities): their candidate pairs
+    win no pixel, so the many-candidate kernel skips their sweeps of the gradient round (and zeroes their pose
+    partials).  Loss, winners and gradients against the oracle on the same modified inputs."""
+    def build():
+        g = Golden("trimin_mixed")
+        for k in list(g.inputs):
+            if isinstance(k, tuple) and k[0] == "color" and k[1] in (2, -2, 3, -3):
+                g.inputs[k] = 1.0 - g.inputs[k] * 0.25
+        return g
+    g = build()
+    ref, aux = O.run(g.inputs, g.outputs, g.opt(), g.noise, num_scales=g.num_scales)
+    ref["loss"].backward()
+    h = build()
+    be = emu_backend("-DBBD_STREAM_RHM=16")
+    be.dll.emu_skipped_sweeps_total.restype = __import__("ctypes").c_long
+    before = be.dll.emu_skipped_sweeps_total()
+    losses, plan = run_fused(h.inputs, h.outputs, h.opt(), h.noise, h.num_scales, backend=be, groups=aux["groups"])
+    assert be.dll.emu_skipped_sweeps_total() > before, "no sweep was skipped: the test does not reach the path it is for"
+    losses["loss"].backward()
+    for k, v in ref.items():
+        assert abs(float(losses[k]) - float(v)) <= 2e-6 * max(1.0, abs(float(v))), k
+    n_checked = 0
+    for k, v in g.params.items():
+        if v.grad is not None:
+            assert rel_l2(h.params[k].grad, v.grad) <= 1e-5 or float(v.grad.abs().max()) == 0.0, k
+            if float(v.grad.abs().max()) == 0.0:   # a pose nothing is warped with successfully: exactly zero here too
+                assert h.params[k].grad is None or float(h.params[k].grad.abs().max()) == 0.0, k
+            n_checked += 1
+    assert n_checked > 0
