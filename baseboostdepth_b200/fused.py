@@ -47,6 +47,32 @@ def _side_streams(device):
     return s
 
 
+def _pose_rows_covered(plan) -> bool:
+    c = getattr(plan, "_pose_rows_covered", None)
+    if c is None:
+        used = set()
+        for b in range(plan.batch):
+            for k in range(int(plan.hdr[b, 0])):
+                used.add(int(plan.rep_tab[b, k, 2]))
+        c = used == set(range(plan.n_pose))
+        try:
+            object.__setattr__(plan, "_pose_rows_covered", c)
+        except Exception:
+            pass
+    return c
+
+
+_NOISE_STREAM: Dict = {}
+
+
+def noise_stream(device):
+    """Helper stream of the tie-break noise draws (trainer.draw_noise)."""
+    s = _NOISE_STREAM.get(device)
+    if s is None:
+        s = _NOISE_STREAM[device] = torch.cuda.Stream(device=device)
+    return s
+
+
 def _call(be, timers, key, name, *args):
     """``be.call`` with an optional pair of CUDA events around it on the stream it is enqueued on
     (bench.py's per-kernel table); ``timers[key]`` = (start, end)."""
@@ -283,7 +309,11 @@ class _FusedLoss(torch.autograd.Function):
         ra.min_rep, ra.force_tile = min(len(r) for r in plan.rep), int(_FORCE_TILE)
         # the streaming kernel reduces its own partials (last warp of every (scale, sample), fixed order)
         reproj = torch.empty(S, **f32)
-        gpose = torch.zeros(S, plan.n_pose, 3, 4, **f32) if need_grad else None
+        # every pose row belongs to exactly one (sample, candidate) of the tables, so the reduction writes all of
+        # gpose: no zero fill on the critical path (checked once per plan; a plan with orphan rows gets zeros)
+        gpose = None
+        if need_grad:
+            gpose = (torch.empty if _pose_rows_covered(plan) else torch.zeros)(S, plan.n_pose, 3, 4, **f32)
         fused_finalize = rgba_arr is not None and plan.max_rep <= 2
         if fused_finalize:
             ra.tickets = _tickets(dev, S * B + S).data_ptr()

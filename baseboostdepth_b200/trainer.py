@@ -28,7 +28,7 @@ from typing import Dict, Optional
 
 import torch
 
-from . import _lib
+from . import _lib, fused
 from .fused import _PosePack, combine_losses, fused_losses, pack_poses, start_side_branch
 from .plan import LossPlan, build_plan
 
@@ -82,12 +82,28 @@ def _index_tensor(plan: LossPlan, key, values, device):
     return t
 
 
-def draw_noise(plan: LossPlan, height, width, device):
+def draw_noise(plan: LossPlan, height, width, device, overlap=False):
     """Tie-break noise exactly as the reference draws it: one ``torch.randn`` per group, in
     group order, of the group's plane-stack shape (``trainer.py:518,522``).  Returned raw;
-    the ``* 1e-5`` is applied inside the identity kernel (``noise_scale``)."""
-    return {g: torch.randn((len(plan.group_members[g]), 1, height, width), device=device)
-            for g in plan.groups}
+    the ``* 1e-5`` is applied inside the identity kernel (``noise_scale``).
+
+    ``overlap`` (CUDA): the draws run on a helper stream next to the pose packing (same generator, same order,
+    hence the same numbers); returns ``(noise, event)`` and the caller makes the launch stream wait for
+    ``event`` before the identity pre-pass."""
+    shapes = {g: (len(plan.group_members[g]), 1, height, width) for g in plan.groups}
+    if not (overlap and torch.device(device).type == "cuda" and fused._USE_SIDE):
+        return {g: torch.randn(shapes[g], device=device) for g in plan.groups}, None
+    main, side = torch.cuda.current_stream(), fused.noise_stream(torch.device(device))
+    noise = {g: torch.empty(shapes[g], device=device) for g in plan.groups}  # allocated on the launch stream
+    fork = torch.cuda.Event()
+    fork.record(main)
+    side.wait_event(fork)
+    with torch.cuda.stream(side):
+        for g in plan.groups:
+            noise[g].normal_()
+        done = torch.cuda.Event()
+        done.record(side)
+    return noise, done
 
 
 def loss_step(inputs, outputs, opt, plan: Optional[LossPlan] = None, noise=None, num_scales=None,
@@ -117,6 +133,12 @@ def loss_step(inputs, outputs, opt, plan: Optional[LossPlan] = None, noise=None,
     # disparity -> depth and the smoothness kernels start first, on the helper stream; the pose packing,
     # the noise draw and the identity pre-pass below run next to them
     be = backend if backend is not None else _lib.cuda_backend()
+    noise_ready = None
+    if noise is None:
+        noise, noise_ready = draw_noise(plan, H, W, color0.device, overlap=be.cuda)
+        noise_scale = 0.00001
+    else:
+        noise_scale = 1.0
     pre = start_side_branch(be, disps, pyramid, (B, H, W), opt.min_depth, opt.max_depth, getattr(opt, "SQL", False),
                             torch.is_grad_enabled(), timers=timers)
 
@@ -124,10 +146,8 @@ def loss_step(inputs, outputs, opt, plan: Optional[LossPlan] = None, noise=None,
     T_err = _frame_poses(plan, inputs, outputs, "cam_T_cam_error", row_masks) if plan.decomp else None
     P = pack_poses(plan, inputs[("K", 0)], T, T_err, backend=backend)
     frames = {f: inputs[("color", f, 0)] for f in plan.frames}
-    if noise is None:
-        noise, noise_scale = draw_noise(plan, H, W, color0.device), 0.00001
-    else:
-        noise_scale = 1.0
+    if noise_ready is not None:
+        torch.cuda.current_stream().wait_event(noise_ready)
 
     reproj, smooth, aux = fused_losses(
         plan, color0, frames, disps, inputs[("inv_K", 0)], P, noise, pyramid,
