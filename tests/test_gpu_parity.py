@@ -66,6 +66,52 @@ def test_golden_case_on_gpu(case, cuda_device):
         assert max_abs(h.outputs[("color", f, s0)], g.ref_out[("color", f, s0)]) <= 2e-5, f
 
 
+def test_far_baselines_that_never_win_on_gpu(cuda_device):
+    """Tri-min batch at frame size whose +-2 / +-3 frames are far from the target: their candidate pairs win nowhere,
+    the many-candidate kernel skips their sweeps of the gradient round.  Loss, selections and gradients against the
+    oracle on the same inputs; the poses of the skipped candidates get exactly zero gradient."""
+    cfg = dict(batch=4, height=192, width=640, baselines=[3, 2, 1, 3], trimin=True, decomp=False)
+    scales = [0, 1, 2, 3]
+    opt = O.default_opt(height=192, width=640, trimin=True, decomp=False, pose_error=5.5, scales=scales, batch_size=4)
+
+    def build():
+        inputs, outputs, params = make_batch(seed=21, device="cpu", scales=scales, **cfg)
+        for k in list(inputs):
+            if isinstance(k, tuple) and k[0] == "color" and k[1] in (2, -2, 3, -3):
+                inputs[k] = inputs[k] + 3.0
+        return inputs, outputs, params
+    inputs, outputs, params = build()
+    plan = plan_for(inputs["ordering"], True, False, None)
+    noise = make_noise(plan, 192, 640, seed=22)
+    retain_pose_grads(outputs)
+    ref, aux = O.run(inputs, outputs, opt, noise, num_scales=4)
+    ref["loss"].backward()
+    i64, o64, p64 = make_batch(seed=21, device="cpu", dtype=torch.float64, scales=scales, **cfg)
+    for k in list(i64):
+        if isinstance(k, tuple) and k[0] == "color" and k[1] in (2, -2, 3, -3):
+            i64[k] = i64[k] + 3.0
+    retain_pose_grads(o64)
+    ref64, _ = O.run(i64, o64, opt, {k: v.double() for k, v in noise.items()}, num_scales=4)
+    ref64["loss"].backward()
+    gi, go, leaves = mirror_to_device(inputs, outputs, params, cuda_device)
+    losses, plan = run_fused(gi, go, opt, {k: v.to(cuda_device) for k, v in noise.items()}, 4, groups=aux["groups"])
+    losses["loss"].backward()
+    torch.cuda.synchronize()
+    for k in ref:
+        assert abs(float(losses[k]) - float(ref[k])) <= 2e-6 * max(1.0, abs(float(ref[k]))), k
+    _selection_check(go["argmin"], plan, aux, scales)
+    zero_poses = 0
+    for k, leaf in leaves.items():
+        want = params[k].grad if k[0] == "disp" else outputs[k].grad
+        if float(want.abs().max()) == 0.0:
+            assert float(leaf.grad.abs().max()) == 0.0, k
+            zero_poses += 1
+        else:
+            r64 = p64[k].grad if k[0] == "disp" else o64[k].grad
+            assert_grad_parity(leaf.grad, want, r64, k, case="far_baselines_640x192_b4")
+    assert zero_poses > 0   # the far frames' poses: nothing was warped with them successfully
+
+
 FULL = [
     ("config2_640x192_b4", dict(batch=4, height=192, width=640, baselines=[1] * 4, trimin=False, decomp=False)),
     ("config3a_trimin_mixed_b4", dict(batch=4, height=192, width=640, baselines=[3, 2, 1, "s"], trimin=True,
