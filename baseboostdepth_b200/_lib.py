@@ -126,7 +126,7 @@ class Backend:
         if self.cuda:
             args = args + (self.stream(),)
         rc = fn(*args)
-        self.launches += {"smooth_fused": 2, "grid_sample_backward_image": 2}.get(name, 1)
+        self.launches += {"grid_sample_backward_image": 2}.get(name, 1)
         if rc != 0:
             msg = self.dll.bbd_last_error_string().decode() if self.cuda else ""
             raise RuntimeError(f"bbd_{name} failed with code {rc}: {msg}")

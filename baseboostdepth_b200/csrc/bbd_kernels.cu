@@ -347,40 +347,26 @@ __global__ void __launch_bounds__(FIN_NT) reproj_finalize_kernel(const bbd_repro
 // ------------------------------------------------------------------------------------------
 // smoothness
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SM_NT) smooth_stage1_kernel(const SmoothArgs a) {
-  __shared__ float red[SM_NT + SM_NT / 16];
-  const int lvl = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
-  if (chunk >= sm_chunks(a.h[lvl], a.w[lvl])) return;
-  sm_park(red, tid, sm_stage1_thread(a, lvl, b, chunk, tid));
-  __syncthreads();
-  sm_l1(red, tid);
-  __syncthreads();
-  if (tid == 0) sm_slot(a, lvl, b, 0)[chunk] = sm_l2(red);
-}
-
 // grid (column blocks, row chunks, levels * B); 4 warps x 30 owned columns per block.  The last block to
 // take a ticket reduces the partials (fixed order) to the level losses and the per-sample scalars.
 __global__ void __launch_bounds__(SMR_WARPS * 32) smooth_rows_kernel(const SmoothArgs a, float* coef, unsigned* ticket, unsigned total) {
-  __shared__ float red[SMR_WARPS][3];
-  __shared__ float mean_s;
+  __shared__ float red[SMR_WARPS][4];
   __shared__ int last_s;
   __shared__ float tx_s[BBD_MAX_SCALES * 256], ty_s[BBD_MAX_SCALES * 256];
   const int lvl = blockIdx.z / a.batch, b = blockIdx.z - lvl * a.batch, bx = blockIdx.x, by = blockIdx.y;
   const int nbx = smr_nbx(a.w[lvl]);
   if (bx >= nbx || by >= smr_nby(a.h[lvl])) return;  // block-uniform
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) mean_s = a.normalize ? sm_sample_mean(a, lvl, b) : 0.0f;
-  __syncthreads();
-  float out[3];
-  sm_rows_lane(a, lvl, b, bx, by, warp, lane, mean_s, out);
-  if (lane == 0) { red[warp][0] = out[0]; red[warp][1] = out[1]; red[warp][2] = out[2]; }
+  float out[4];
+  sm_rows_lane(a, lvl, b, bx, by, warp, lane, out);
+  if (lane == 0) { red[warp][0] = out[0]; red[warp][1] = out[1]; red[warp][2] = out[2]; red[warp][3] = out[3]; }
   __syncthreads();
   if (tid == 0) {
     const int slot = by * nbx + bx;
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 4; ++k) {
       float v = 0.0f;
       for (int w = 0; w < SMR_WARPS; ++w) v += red[w][k];
-      sm_slot(a, lvl, b, 1 + k)[slot] = v;
+      sm_slot(a, lvl, b, k < 3 ? 1 + k : 0)[slot] = v;  // slots 1..3: loss and coupling sums, slot 0: sum of the disparity
     }
     __threadfence();
     last_s = (atomicAdd(ticket, 1u) == total - 1u) ? 1 : 0;
@@ -968,10 +954,6 @@ int bbd_smooth_fused(const bbd_smooth_args* in, bbd_stream_t stream) {
   unsigned* ticket = reinterpret_cast<unsigned*>(tail + (size_t)a.levels * a.batch * 2);
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(ticket, 0, sizeof(unsigned), st);
-  if (a.normalize) {
-    dim3 grid1(mc, a.batch, a.levels);
-    smooth_stage1_kernel<<<grid1, SM_NT, 0, st>>>(a);
-  }
   dim3 grid(nbx, nby, a.levels * a.batch);
   smooth_rows_kernel<<<grid, SMR_WARPS * 32, 0, st>>>(a, coef, ticket, total);
   if (!a.defer_norm && a.normalize) {

@@ -1,12 +1,14 @@
 // Edge-aware smoothness on mean-normalised disparity, forward + backward.
 //
 // Reference: trainer.py:560-564 (norm_disp = disp / (mean_hw(disp) + 1e-7)) and
-// get_smooth_loss, layers.py:203-216.  All pyramid levels are handled by one launch per
-// stage (grid.z = level); the three stages are separated by kernel boundaries because
-// the mean normalisation couples every pixel of a sample:
-//   stage 1  per-chunk sums of disp                      -> sample mean m
-//   stage 2  per-pixel terms, loss partials, g_d = dL/d(norm disp), partials of sum(g_d * disp)
-//   stage 3  g_disp = g_d / (m+eps) - sum(g_d*disp) / (N (m+eps)^2); level loss
+// get_smooth_loss, layers.py:203-216.  The mean normalisation couples every pixel of a sample, but only
+// through one positive scalar r = 1 / (mean + eps): |d_x (r d)| = r |d_x d| and sign(d_x (r d)) = sign(d_x d),
+// so ONE pass over the planes (all pyramid levels in one launch) works on the raw disparity and accumulates
+//   sum d, sum |dx d| e, sum |dy d| e, sum g_d * d   per block, and writes g_d = dL/d(norm disp);
+// the last block to finish reduces the partials (fixed order), forms the sample means, scales the loss sums by
+// r and leaves the two per-sample scalars that turn g_d into the gradient w.r.t. the raw disparity
+//   g_disp = g_d / (m+eps) - sum(g_d*disp) / (N (m+eps)^2)
+// (applied by the disparity backward on the fly, or by sm_apply_px for stand-alone callers).
 // Same host/device phase structure as bbd_strip.cuh.
 #pragma once
 #include "bbd_common.cuh"
@@ -92,13 +94,11 @@ BBD_HD float smr_xor(float v, int) { return v; }
 BBD_HD float smr_sign(float d) { return d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f); }
 
 // one lane of one warp: out[3] = warp totals (valid in every lane)
-BBD_HD void sm_rows_lane(const SmoothArgs& a, int lvl, int b, int bx, int by, int warp, int lane, float mean, float out[3]) {
+BBD_HD void sm_rows_lane(const SmoothArgs& a, int lvl, int b, int bx, int by, int warp, int lane, float out[4]) {
   const int h = a.h[lvl], w = a.w[lvl], n = h * w;
   const float* d = a.disp[lvl] + (size_t)b * n;
   const float* img = a.img[lvl] + (size_t)b * 3 * n;
   float* g = a.gdisp[lvl] ? a.gdisp[lvl] + (size_t)b * n : nullptr;
-  const float den = a.normalize ? mean + 1e-7f : 1.0f;
-  const float rden = 1.0f / den;
   const float inx = 1.0f / ((float)a.batch * (float)h * (float)(w - 1));
   const float iny = 1.0f / ((float)a.batch * (float)(h - 1) * (float)w);
   const int x = (bx * SMR_WARPS + warp) * SMR_TW + lane - 1;
@@ -107,12 +107,12 @@ BBD_HD void sm_rows_lane(const SmoothArgs& a, int lvl, int b, int bx, int by, in
   const int xc = x < 0 ? 0 : (x >= w ? w - 1 : x);
   const int y0 = by * SMR_RC, y1 = (y0 + SMR_RC < h) ? y0 + SMR_RC : h;
   const int ys = y0 > 0 ? y0 - 1 : 0;  // one row above the chunk seeds the vertical term
-  float stx = 0.0f, sty = 0.0f, sgd = 0.0f, sy_prev = 0.0f;
+  float stx = 0.0f, sty = 0.0f, sgd = 0.0f, sd = 0.0f, sy_prev = 0.0f;
   float dn = d[ys * w + xc], In[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) In[c] = img[c * n + ys * w + xc];
   for (int y = ys; y < y1; ++y) {
-    const float draw = dn, d0 = draw * rden;
+    const float draw = dn, d0 = draw;  // raw disparity: the normalisation is a positive scale applied at the end
     float I0[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) I0[c] = In[c];
@@ -130,7 +130,7 @@ BBD_HD void sm_rows_lane(const SmoothArgs& a, int lvl, int b, int bx, int by, in
     const bool has_r = valid && x < w - 1 && lane < 31, has_d = y < h - 1;
     const float ex = has_r ? expf(-ax * BBD_THIRD) : 0.0f;
     const float ey = has_d ? expf(-ay * BBD_THIRD) : 0.0f;
-    const float dfx = d0 - dr, dfy = d0 - dn * rden;
+    const float dfx = d0 - dr, dfy = d0 - dn;
     const float sx = smr_sign(dfx) * ex * inx, sy = smr_sign(dfy) * ey * iny;
     const float sx_up = smr_up(sx);
     const float sxl = (lane > 0 && x > 0) ? sx_up : 0.0f;
@@ -140,6 +140,7 @@ BBD_HD void sm_rows_lane(const SmoothArgs& a, int lvl, int b, int bx, int by, in
       stx += fabsf(dfx) * ex;
       sty += fabsf(dfy) * ey;
       sgd += gd * draw;
+      sd += draw;
     }
     sy_prev = sy;
   }
@@ -148,26 +149,30 @@ BBD_HD void sm_rows_lane(const SmoothArgs& a, int lvl, int b, int bx, int by, in
     stx += smr_xor(stx, m);
     sty += smr_xor(sty, m);
     sgd += smr_xor(sgd, m);
+    sd += smr_xor(sd, m);
   }
   out[0] = stx;
   out[1] = sty;
   out[2] = sgd;
+  out[3] = sd;
 }
 
 // fixed-order reduction of the block partials of one (level, sample): thread-serial, tiny
 BBD_HD void sm_finish_sample(const SmoothArgs& a, int lvl, int b, float* coef, float sums[2]) {
   const int nb = smr_blocks(a.h[lvl], a.w[lvl]);
+  const float* p0 = sm_slot(a, lvl, b, 0);
   const float* p1 = sm_slot(a, lvl, b, 1);
   const float* p2 = sm_slot(a, lvl, b, 2);
   const float* p3 = sm_slot(a, lvl, b, 3);
-  float tx = 0.0f, ty = 0.0f, gd = 0.0f;
-  for (int i = 0; i < nb; ++i) { tx += p1[i]; ty += p2[i]; gd += p3[i]; }
-  sums[0] = tx;
-  sums[1] = ty;
+  float tx = 0.0f, ty = 0.0f, gd = 0.0f, sd = 0.0f;
+  for (int i = 0; i < nb; ++i) { tx += p1[i]; ty += p2[i]; gd += p3[i]; sd += p0[i]; }
+  const int n = a.h[lvl] * a.w[lvl];
+  const float den = a.normalize ? sd / (float)n + 1e-7f : 1.0f;
+  const float rden = 1.0f / den;
+  sums[0] = tx * rden;
+  sums[1] = ty * rden;
   if (coef) {
-    const int n = a.h[lvl] * a.w[lvl];
-    const float den = a.normalize ? sm_sample_mean(a, lvl, b) + 1e-7f : 1.0f;
-    coef[((size_t)lvl * a.batch + b) * 2] = 1.0f / den;
+    coef[((size_t)lvl * a.batch + b) * 2] = rden;
     coef[((size_t)lvl * a.batch + b) * 2 + 1] = a.normalize ? gd / ((float)n * den * den) : 0.0f;
   }
 }

@@ -285,34 +285,23 @@ int emu_smooth_fused(const bbd_smooth_args* in) {
   a.max_chunks = mc;
   float* tail = a.scratch + (size_t)a.levels * a.batch * 4 * mc;
   float* coef = a.defer_norm ? a.coef : tail;
-  std::vector<float> red(SM_NT + SM_NT / 16), v(SM_NT);
-  if (a.normalize)
-    for (int lvl = 0; lvl < a.levels; ++lvl)
-      for (int b = 0; b < a.batch; ++b)
-        for (int c = 0; c < sm_chunks(a.h[lvl], a.w[lvl]); ++c) {
-          for (int tid = 0; tid < SM_NT; ++tid) v[tid] = sm_stage1_thread(a, lvl, b, c, tid);
-          for (int tid = 0; tid < SM_NT; ++tid) sm_park(red.data(), tid, v[tid]);
-          for (int tid = 0; tid < SM_NT; ++tid) sm_l1(red.data(), tid);
-          sm_slot(a, lvl, b, 0)[c] = sm_l2(red.data());
-        }
   // stage 2: one fiber block per warp of the device kernel's blocks
   for (int lvl = 0; lvl < a.levels; ++lvl)
     for (int b = 0; b < a.batch; ++b) {
-      const float mean = a.normalize ? sm_sample_mean(a, lvl, b) : 0.0f;
       const int nbx = smr_nbx(a.w[lvl]), nby = smr_nby(a.h[lvl]);
       for (int by = 0; by < nby; ++by)
         for (int bx = 0; bx < nbx; ++bx) {
-          float tot[3] = {0.0f, 0.0f, 0.0f};
+          float tot[4] = {0.0f, 0.0f, 0.0f, 0.0f};
           for (int warp = 0; warp < SMR_WARPS; ++warp) {
-            float out[3];
+            float out[4];
             simt::run_block(32, [&](int tid) {
-              float o[3];
-              sm_rows_lane(a, lvl, b, bx, by, warp, tid, mean, o);
-              if (tid == 0) { out[0] = o[0]; out[1] = o[1]; out[2] = o[2]; }
+              float o[4];
+              sm_rows_lane(a, lvl, b, bx, by, warp, tid, o);
+              if (tid == 0) { out[0] = o[0]; out[1] = o[1]; out[2] = o[2]; out[3] = o[3]; }
             });
-            for (int k = 0; k < 3; ++k) tot[k] += out[k];
+            for (int k = 0; k < 4; ++k) tot[k] += out[k];
           }
-          for (int k = 0; k < 3; ++k) sm_slot(a, lvl, b, 1 + k)[by * nbx + bx] = tot[k];
+          for (int k = 0; k < 4; ++k) sm_slot(a, lvl, b, k < 3 ? 1 + k : 0)[by * nbx + bx] = tot[k];
         }
     }
   std::vector<float> tx(a.levels * a.batch), ty(a.levels * a.batch);
