@@ -25,39 +25,8 @@ BBD_HD float* sm_slot(const SmoothArgs& a, int lvl, int b, int which) {
   return a.scratch + (((size_t)lvl * a.batch + b) * 4 + which) * a.max_chunks;
 }
 
-// fixed-order block sum of one value per thread via shared memory (red: [NT + NT/16])
-BBD_HD void sm_park(float* red, int tid, float v) { red[tid] = v; }
-BBD_HD void sm_l1(float* red, int tid) {
-  if (tid < SM_NT / 16) {
-    float s = 0.0f;
-    for (int i = 0; i < 16; ++i) s += red[tid * 16 + i];
-    red[SM_NT + tid] = s;
-  }
-}
-BBD_HD float sm_l2(const float* red) {
-  float s = 0.0f;
-  for (int i = 0; i < SM_NT / 16; ++i) s += red[SM_NT + i];
-  return s;
-}
-
-BBD_HD float sm_stage1_thread(const SmoothArgs& a, int lvl, int b, int chunk, int tid) {
-  const int n = a.h[lvl] * a.w[lvl];
-  const float* d = a.disp[lvl] + (size_t)b * n;
-  float s = 0.0f;
-  for (int i = chunk * SM_CHUNK + tid; i < (chunk + 1) * SM_CHUNK && i < n; i += SM_NT) s += d[i];
-  return s;
-}
-
-BBD_HD float sm_sample_mean(const SmoothArgs& a, int lvl, int b) {
-  const float* p = sm_slot(a, lvl, b, 0);
-  const int nc = sm_chunks(a.h[lvl], a.w[lvl]);
-  float s = 0.0f;
-  for (int i = 0; i < nc; ++i) s += p[i];
-  return s / (float)(a.h[lvl] * a.w[lvl]);
-}
-
 // ---------------------------------------------------------------------------------------------------
-// Stage 2 in row-walking form (round 2).  A warp owns 30 columns (lanes 1..30; lanes 0 and 31 are the
+// The pass in row-walking form (round 2).  A warp owns 30 columns (lanes 1..30; lanes 0 and 31 are the
 // neighbours' columns) of a chunk of rows and walks down: every edge weight exp(-mean_c |dI|) is
 // evaluated once and handed to the pixel on its other side by a shuffle (x) or kept in a register for
 // the next row (y); no div/mod per pixel.  Writes g_d = dL/d(norm disp) and per-block partial sums
