@@ -209,18 +209,18 @@ __global__ void __launch_bounds__(SCfg::NT, BBD_MIN_BLOCKS) reproj_kernel(const 
 #ifndef BBD_STREAM_MINB
 #define BBD_STREAM_MINB 8
 #endif
-template <int K, bool GRAD, bool MULTI>
+template <int K, bool GRAD, bool MULTI, bool WING = false>
 __global__ void __launch_bounds__(BBD_STREAM_WARPS * 32, BBD_STREAM_MINB) reproj_stream_kernel(const bbd_reproj_args a, int n_units, int part_stride, int seg_rows) {
   extern __shared__ __align__(128) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x * BBD_STREAM_WARPS + warp;
   if (unit >= n_units) return;  // warp-uniform
   StreamTmaMaps none = {nullptr, nullptr, nullptr};
-  stream_unit<K, GRAD, false, MULTI>(a, unit, lane, smem + (size_t)warp * StreamSmem<K, false, MULTI>::FLOATS, part_stride, none, seg_rows);
+  stream_unit<K, GRAD, false, MULTI, WING>(a, unit, lane, smem + (size_t)warp * StreamSmem<K, false, MULTI, GRAD, MULTI && !WING>::FLOATS, part_stride, none, seg_rows);
 }
 
 // The same kernel with the strip's regular planes (target, depth, identity minimum) staged by the TMA unit.
-template <int K, bool GRAD, bool MULTI>
+template <int K, bool GRAD, bool MULTI, bool WING = false>
 __global__ void __launch_bounds__(BBD_STREAM_WARPS * 32, BBD_STREAM_MINB)
     reproj_stream_tma_kernel(const bbd_reproj_args a, int n_units, int part_stride, const __grid_constant__ CUtensorMap tm_tgt,
                              const __grid_constant__ CUtensorMap tm_dep, const __grid_constant__ CUtensorMap tm_idm, int seg_rows) {
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(BBD_STREAM_WARPS * 32, BBD_STREAM_MINB)
   const int unit = blockIdx.x * BBD_STREAM_WARPS + warp;
   if (unit >= n_units) return;  // warp-uniform
   StreamTmaMaps maps = {&tm_tgt, &tm_dep, &tm_idm};
-  stream_unit<K, GRAD, true, MULTI>(a, unit, lane, smem + (size_t)warp * StreamSmem<K, true, MULTI>::FLOATS, part_stride, maps, seg_rows);
+  stream_unit<K, GRAD, true, MULTI, WING>(a, unit, lane, smem + (size_t)warp * StreamSmem<K, true, MULTI, GRAD, MULTI && !WING>::FLOATS, part_stride, maps, seg_rows);
 }
 
 // The pipelined form (bbd_pipe.cuh): one block = one unit, its warps are the gather / statistics / backward
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256) pack_rgba_scalar_kernel(int n, int HW, co
 // 768 threads = 64 tile-lanes x 12 components: every thread adds its share of the partials, a
 // fixed-order tail adds the lanes (deterministic, no atomics).
 constexpr int FIN_NT = 768, FIN_LANES = FIN_NT / 12;
-__global__ void __launch_bounds__(FIN_NT) reproj_finalize_kernel(const bbd_reproj_args a, float* loss, float* gpose, int ntiles, int used) {
+__global__ void __launch_bounds__(FIN_NT) reproj_finalize_kernel(const bbd_reproj_args a, float* loss, float* gpose, int ntiles, int used, int used_grad) {
   __shared__ float red[FIN_NT];
   __shared__ float red2[32];
   const int tid = threadIdx.x;
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(FIN_NT) reproj_finalize_kernel(const bbd_repro
     for (int k = 0; k < n_rep; ++k) {
       if (a.tab.rep[((size_t)b * BBD_MAX_REP + k) * 4 + 2] != pose) continue;
       const float* p = a.gpose_part + (((size_t)s * a.batch + b) * BBD_MAX_REP + k) * ntiles * 12;
-      for (int tI = lane; tI < used; tI += FIN_LANES) acc += p[(size_t)tI * 12 + comp];
+      for (int tI = lane; tI < used_grad; tI += FIN_LANES) acc += p[(size_t)tI * 12 + comp];
     }
   }
   red[tid] = acc;
@@ -727,11 +727,18 @@ static int stream_slots() {
   return slots;
 }
 static int seg_rows_for(const bbd_reproj_args* a) {
+  if (a->max_rep > 2) return stream_seg_rows_uneven(a->height, a->width, a->num_scales * a->batch, stream_slots());
   return stream_seg_rows(a->height, a->width, a->num_scales * a->batch, stream_slots());
 }
-static int parts_used(const bbd_reproj_args* a) {
+// The many-candidate form with gradients runs as two launches when the caller provides the winner plane: a forward-only
+// selection launch (twelve warps per SM) and a gradient launch that reads the winners (tall segments).
+static bool split_multi(const bbd_reproj_args* a) {
+  return use_stream(a) && a->max_rep > 2 && a->need_grad && a->winner != nullptr;
+}
+// slots of loss_part / gpose_part a launch fills per (scale, sample): the two can differ in the split form
+static int parts_used(const bbd_reproj_args* a, bool grad_parts) {
   if (!use_stream(a)) return tile_parts(a->height, a->width);
-  if (a->max_rep > 2) return StreamGeoM::units(a->height, a->width);
+  if (a->max_rep > 2 && !(grad_parts && split_multi(a))) return StreamGeoM::units(a->height, a->width);
   const int rh = seg_rows_for(a);
   return StreamGeo::strips(a->width) * ((a->height + rh - 1) / rh);
 }
@@ -780,11 +787,11 @@ static bool use_pipe() {
   return e ? (e[0] != '0') : (BBD_USE_PIPE != 0);
 }
 
-template <int K, bool GRAD, bool MULTI>
+template <int K, bool GRAD, bool MULTI, bool WING = false>
 static int launch_stream(const bbd_reproj_args* a, cudaStream_t stream) {
-  const int n_units = a->num_scales * a->batch * parts_used(a);
+  const int n_units = a->num_scales * a->batch * parts_used(a, WING);
   const int blocks = (n_units + BBD_STREAM_WARPS - 1) / BBD_STREAM_WARPS;
-  const int seg_rows = MULTI ? BBD_STREAM_RHM : seg_rows_for(a);
+  const int seg_rows = (MULTI && !WING) ? BBD_STREAM_RHM : seg_rows_for(a);
   const int stride = bbd_reproj_tiles(a->height, a->width);
 #if BBD_STREAM_TMA
   CUtensorMap tt, td, ti;
@@ -803,25 +810,25 @@ static int launch_stream(const bbd_reproj_args* a, cudaStream_t stream) {
       return check_launch("reproj_pipe_kernel");
     }
     static bool configured = false;
-    constexpr size_t smem = (size_t)BBD_STREAM_WARPS * StreamSmem<K, true, MULTI>::FLOATS * sizeof(float);
+    constexpr size_t smem = (size_t)BBD_STREAM_WARPS * StreamSmem<K, true, MULTI, GRAD, MULTI && !WING>::FLOATS * sizeof(float);
     if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(reproj_stream_tma_kernel<K, GRAD, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = cudaFuncSetAttribute(reproj_stream_tma_kernel<K, GRAD, MULTI, WING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return fail((int)e, "reproj_stream_tma_kernel: shared memory attribute");
       configured = true;
     }
-    reproj_stream_tma_kernel<K, GRAD, MULTI><<<blocks, BBD_STREAM_WARPS * 32, smem, stream>>>(*a, n_units, stride, tt, td, ti, seg_rows);
+    reproj_stream_tma_kernel<K, GRAD, MULTI, WING><<<blocks, BBD_STREAM_WARPS * 32, smem, stream>>>(*a, n_units, stride, tt, td, ti, seg_rows);
     return check_launch("reproj_stream_tma_kernel");
   }
 #endif
   // widths that are not a multiple of four floats (or unaligned planes) cannot be described to the TMA unit
   static bool configured = false;
-  constexpr size_t smem = (size_t)BBD_STREAM_WARPS * StreamSmem<K, false, MULTI>::FLOATS * sizeof(float);
+  constexpr size_t smem = (size_t)BBD_STREAM_WARPS * StreamSmem<K, false, MULTI, GRAD, MULTI && !WING>::FLOATS * sizeof(float);
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(reproj_stream_kernel<K, GRAD, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(reproj_stream_kernel<K, GRAD, MULTI, WING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "reproj_stream_kernel: shared memory attribute");
     configured = true;
   }
-  reproj_stream_kernel<K, GRAD, MULTI><<<blocks, BBD_STREAM_WARPS * 32, smem, stream>>>(*a, n_units, stride, seg_rows);
+  reproj_stream_kernel<K, GRAD, MULTI, WING><<<blocks, BBD_STREAM_WARPS * 32, smem, stream>>>(*a, n_units, stride, seg_rows);
   return check_launch("reproj_stream_kernel");
 }
 
@@ -867,6 +874,10 @@ int bbd_reproj_fused(const bbd_reproj_args* a, bbd_stream_t stream) {
     if (a->max_rep == 1) return a->need_grad ? launch_stream<1, true, false>(a, st) : launch_stream<1, false, false>(a, st);
     if (a->max_rep == 2) return a->need_grad ? launch_stream<2, true, false>(a, st) : launch_stream<2, false, false>(a, st);
 #if !BBD_STREAM_ASYNC
+    if (split_multi(a)) {  // selection round, then the gradient round reading a->winner
+      if (int rc = launch_stream<2, false, true>(a, st)) return rc;
+      return launch_stream<2, true, true, true>(a, st);
+    }
     return a->need_grad ? launch_stream<2, true, true>(a, st) : launch_stream<2, false, true>(a, st);
 #endif
   }
@@ -906,8 +917,11 @@ const char* bbd_reproj_kernel_name(const bbd_reproj_args* a) {
     if (tma && a->max_rep <= 2 && use_pipe())
       snprintf(name, sizeof(name), "bbd::reproj_pipe_kernel<%d, %d>", a->max_rep == 1 ? 1 : 2, a->need_grad ? 1 : 0);
     else
-      snprintf(name, sizeof(name), "bbd::reproj_stream%s_kernel<%d, %d, %d>", tma ? "_tma" : "", a->max_rep == 1 ? 1 : 2, a->need_grad ? 1 : 0,
-               a->max_rep > 2 ? 1 : 0);
+      if (split_multi(a))  // selection launch <2, 0, 1> followed by the gradient launch named here
+        snprintf(name, sizeof(name), "bbd::reproj_stream%s_kernel<2, 1, 1, 1>", tma ? "_tma" : "");
+      else
+        snprintf(name, sizeof(name), "bbd::reproj_stream%s_kernel<%d, %d, %d>", tma ? "_tma" : "", a->max_rep == 1 ? 1 : 2, a->need_grad ? 1 : 0,
+                 a->max_rep > 2 ? 1 : 0);
     return name;
   }
   const bool keep = StripSmem<SCfg>::floats(a->max_rep) * sizeof(float) <= 75 * 1024;
@@ -920,7 +934,7 @@ int bbd_reproj_finalize(const bbd_reproj_args* a, float* loss, float* gpose, bbd
   if (gpose && !a->gpose_part) return fail(BBD_E_ARG, "finalize: no pose partials");
   const int ntiles = bbd_reproj_tiles(a->height, a->width);
   const int blocks = a->num_scales * (1 + (gpose ? a->num_pose : 0));
-  reproj_finalize_kernel<<<blocks, FIN_NT, 0, (cudaStream_t)stream>>>(*a, loss, gpose, ntiles, parts_used(a));
+  reproj_finalize_kernel<<<blocks, FIN_NT, 0, (cudaStream_t)stream>>>(*a, loss, gpose, ntiles, parts_used(a, false), parts_used(a, true));
   return check_launch("reproj_finalize_kernel");
 }
 

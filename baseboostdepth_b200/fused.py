@@ -296,7 +296,10 @@ class _FusedLoss(torch.autograd.Function):
         loss_part = torch.empty(S, B, ntiles, **f32)
         gpose_part = torch.empty(S, B, _lib.MAX_REP, ntiles, 12, **f32) if need_grad else None
         gdepth = torch.empty(S, B, H, W, **f32) if need_grad else None
-        winner = torch.empty(S, B, H, W, device=dev, dtype=torch.uint8) if want_winner else None
+        # batches with more than two candidates per sample run as a selection launch and a gradient launch that reads the
+        # per-pixel winners: the plane is needed even when the caller does not ask for it
+        need_winner = want_winner or (need_grad and plan.max_rep > 2 and rgba_arr is not None)
+        winner = torch.empty(S, B, H, W, device=dev, dtype=torch.uint8) if need_winner else None
         ra = _lib.ReprojArgs()
         ra.batch, ra.height, ra.width, ra.num_scales = B, H, W, S
         ra.no_ssim, ra.need_grad, ra.max_rep, ra.num_pose = int(cfg["no_ssim"]), int(need_grad), plan.max_rep, plan.n_pose

@@ -64,10 +64,15 @@ static bool use_stream(const bbd_reproj_args* a) {
   }
   return any;
 }
-static int parts_used(const bbd_reproj_args* a) {
+// same choices as the launcher in bbd_kernels.cu
+static bool split_multi(const bbd_reproj_args* a) {
+  return use_stream(a) && a->max_rep > 2 && a->need_grad && a->winner != nullptr;
+}
+static int parts_used(const bbd_reproj_args* a, bool grad_parts) {
   if (!use_stream(a)) return tile_parts(a->height, a->width);
-  if (a->max_rep > 2) return StreamGeoM::units(a->height, a->width);
-  const int rh = stream_seg_rows(a->height, a->width, a->num_scales * a->batch, 148 * 8);
+  if (a->max_rep > 2 && !(grad_parts && split_multi(a))) return StreamGeoM::units(a->height, a->width);
+  const int rh = a->max_rep > 2 ? stream_seg_rows_uneven(a->height, a->width, a->num_scales * a->batch, 148 * 8)
+                                : stream_seg_rows(a->height, a->width, a->num_scales * a->batch, 148 * 8);
   return StreamGeo::strips(a->width) * ((a->height + rh - 1) / rh);
 }
 
@@ -94,9 +99,9 @@ int emu_pack_rgba(int32_t n, int32_t H, int32_t W, const float* planar, float* r
 }
 
 }  // extern "C"
-template <int K, bool GRAD, bool MULTI>
+template <int K, bool GRAD, bool MULTI, bool WING = false>
 static void emu_stream(const bbd_reproj_args& a) {
-  const int n_units = a.num_scales * a.batch * parts_used(&a);
+  const int n_units = a.num_scales * a.batch * parts_used(&a, WING);
   const int stride = emu_reproj_tiles(a.height, a.width);
   // like the launcher: the TMA-staged variant when the planes can be described to the TMA unit
 #ifdef BBD_EMU_NO_TMA
@@ -106,7 +111,9 @@ static void emu_stream(const bbd_reproj_args& a) {
 #endif
   std::vector<float> smem(StreamSmem<K, true, MULTI>::FLOATS + StreamSmem<K, false, MULTI>::FLOATS + PipeSmem<K, GRAD>::FLOATS);
   StreamTmaMaps none = {nullptr, nullptr, nullptr};
-  const int seg_rows = MULTI ? BBD_STREAM_RHM : stream_seg_rows(a.height, a.width, a.num_scales * a.batch, 148 * 8);
+  const int seg_rows = (MULTI && !WING) ? BBD_STREAM_RHM
+                       : (MULTI ? stream_seg_rows_uneven(a.height, a.width, a.num_scales * a.batch, 148 * 8)
+                                : stream_seg_rows(a.height, a.width, a.num_scales * a.batch, 148 * 8));
   // like the launcher: the pipelined three-warp form for single-sweep launches when BBD_PIPE=1
   const char* pe = getenv("BBD_PIPE");
   const bool pipe = tma && !MULTI && (pe ? pe[0] != '0' : false);
@@ -117,11 +124,11 @@ static void emu_stream(const bbd_reproj_args& a) {
       continue;
     }
     if (tma) {
-      simt::run_block(32, [&](int tid) { stream_unit<K, GRAD, true, MULTI>(a, unit, tid, smem.data(), stride, none, seg_rows); });
+      simt::run_block(32, [&](int tid) { stream_unit<K, GRAD, true, MULTI, WING>(a, unit, tid, smem.data(), stride, none, seg_rows); });
       continue;
     }
 #endif
-    simt::run_block(32, [&](int tid) { stream_unit<K, GRAD, false, MULTI>(a, unit, tid, smem.data(), stride, none, seg_rows); });
+    simt::run_block(32, [&](int tid) { stream_unit<K, GRAD, false, MULTI, WING>(a, unit, tid, smem.data(), stride, none, seg_rows); });
   }
   (void)tma;
 }
@@ -168,6 +175,7 @@ int emu_reproj_fused(const bbd_reproj_args* ap) {
     if (a.max_rep == 1) { if (a.need_grad) emu_stream<1, true, false>(a); else emu_stream<1, false, false>(a); }
     else if (a.max_rep == 2) { if (a.need_grad) emu_stream<2, true, false>(a); else emu_stream<2, false, false>(a); }
 #if !BBD_STREAM_ASYNC
+    else if (split_multi(&a)) { emu_stream<2, false, true>(a); emu_stream<2, true, true, true>(a); }
     else { if (a.need_grad) emu_stream<2, true, true>(a); else emu_stream<2, false, true>(a); }
 #endif
     return 0;
@@ -243,7 +251,7 @@ int emu_reproj_finalizes_itself(const bbd_reproj_args* a) {
 
 int emu_reproj_finalize(const bbd_reproj_args* ap, float* loss, float* gpose) {
   const bbd_reproj_args& a = *ap;
-  const int ntiles = emu_reproj_tiles(a.height, a.width), used = parts_used(ap);
+  const int ntiles = emu_reproj_tiles(a.height, a.width), used = parts_used(ap, false), used_grad = parts_used(ap, true);
   for (int s = 0; s < a.num_scales; ++s) {
     float tot = 0.0f;
     for (int i = 0; i < a.batch * used; ++i) tot += a.loss_part[(size_t)s * a.batch * ntiles + (size_t)(i / used) * ntiles + (i % used)];
@@ -259,7 +267,7 @@ int emu_reproj_finalize(const bbd_reproj_args* ap, float* loss, float* gpose) {
           for (int k = 0; k < n_rep; ++k) {
             if (a.tab.rep[((size_t)b * BBD_MAX_REP + k) * 4 + 2] != pose) continue;
             const float* p = a.gpose_part + (((size_t)s * a.batch + b) * BBD_MAX_REP + k) * ntiles * 12;
-            for (int tI = 0; tI < used; ++tI) acc += p[(size_t)tI * 12 + c];
+            for (int tI = 0; tI < used_grad; ++tI) acc += p[(size_t)tI * 12 + c];
           }
         }
         gpose[((size_t)s * a.num_pose + pose) * 12 + c] = acc;

@@ -264,7 +264,7 @@ def test_far_baselines_that_never_win():
         g = Golden("trimin_mixed")
         for k in list(g.inputs):
             if isinstance(k, tuple) and k[0] == "color" and k[1] in (2, -2, 3, -3):
-                g.inputs[k] = 1.0 - g.inputs[k] * 0.25
+                g.inputs[k] = g.inputs[k] + 3.0
         return g
     g = build()
     ref, aux = O.run(g.inputs, g.outputs, g.opt(), g.noise, num_scales=g.num_scales)
