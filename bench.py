@@ -265,14 +265,30 @@ def run_ours(args):
     # The path's inputs are disparities and camera motions T (gradients are required for
     # depth/disp and T); the motions become leaves here.  Assembling T from axis-angle/translation is
     # the reference's predict_poses, a "next" row, outside the timed path.
-    leaves = dict(params)
-    for k in list(outputs):
-        if k[0] == "cam_T_cam" and outputs[k].numel():
-            outputs[k] = outputs[k].detach().clone().requires_grad_(True)
-            leaves[k] = outputs[k]
+    leaves = {k: v for k, v in params.items() if k[0] == "disp"}
+    pose_params = {}
+    if args.with_pose:
+        # --with-pose: the leaves are the pose network's outputs (axis-angle, translation); every step assembles the
+        # camera motions with the library's pose kernel (layers.transformation_from_parameters: one launch forward,
+        # one backward per frame instead of the reference's ~40 tiny tensor kernels, layers.py:25-100)
+        from baseboostdepth_b200.layers import transformation_from_parameters as pose_op
+        for k, v in params.items():
+            if k[0] in ("axisangle", "translation"):
+                pose_params[k] = v.detach().clone().requires_grad_(True)
+                leaves[k] = pose_params[k]
+    else:
+        for k in list(outputs):
+            if k[0] == "cam_T_cam" and outputs[k].numel():
+                outputs[k] = outputs[k].detach().clone().requires_grad_(True)
+                leaves[k] = outputs[k]
 
     def rebuild_poses():
-        pass
+        if not args.with_pose:
+            return
+        for f in plan.frames:
+            if f == "s":
+                continue
+            outputs[("cam_T_cam", 0, f)] = pose_op(pose_params[("axisangle", f)], pose_params[("translation", f)], invert=(f < 0))
 
     timers = {}
 
@@ -334,6 +350,12 @@ def run_ours(args):
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
+                if args.with_pose:
+                    # fresh leaves: their gradient-accumulation nodes must not belong to the legacy default stream
+                    # the eager loop above ran on (autograd would make that stream wait for the capturing one)
+                    for k in list(pose_params):
+                        pose_params[k] = pose_params[k].detach().clone().requires_grad_(True)
+                        leaves[k] = pose_params[k]
                 for _ in range(3):
                     for p in leaves.values():
                         p.grad = None
@@ -356,6 +378,9 @@ def run_ours(args):
         except Exception as exc:  # noqa: BLE001
             graph_ms = None
             print(f"graph capture failed: {type(exc).__name__}: {exc}", file=sys.stderr)
+            if os.environ.get("BBD_BENCH_DEBUG"):
+                import traceback
+                traceback.print_exc()
 
     # ---- end to end: pinned host batch -> H2D -> fused loss fwd+bwd -> D2H loss ---------------
     # Every step uploads its whole batch (images, pyramid, K, stereo_T, disparities, camera motions)
@@ -524,7 +549,7 @@ def run_ours(args):
                        "timing": "CUDA events per step on the launch stream, mean over steps, max over ranks; "
                                  + ("the step is captured once and replayed as a CUDA graph" if step_ms != eager_ms
                                     else "eager launches"),
-                       "eager_ms_per_step": eager_ms, "eager_wall_ms_per_step_incl_flush": wall_ms,
+                       "with_pose": bool(args.with_pose), "eager_ms_per_step": eager_ms, "eager_wall_ms_per_step_incl_flush": wall_ms,
                        "cuda_graph_replay_ms_per_step": graph_ms_max if graph_ms is not None else None},
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
