@@ -107,7 +107,9 @@ typedef struct bbd_reproj_args {
   float* loss_part;   /* (S,B,tiles) partial sums of to_optimise */
   float* gpose_part;  /* (S,B,BBD_MAX_REP,tiles,12) partial d/dP sums; may be NULL if !need_grad */
   float* gdepth;      /* (S,B,H,W) d mean_s / d depth_s;        may be NULL if !need_grad */
-  uint8_t* winner;    /* (S,B,H,W) argmin index in candidate order (reproj..., then ident...); may be NULL */
+  uint8_t* winner;    /* (S,B,H,W) argmin index in candidate order (reproj..., then ident...); may be NULL.  With
+                       * max_rep > 2 and need_grad a non-NULL plane lets the call run as a forward-only selection
+                       * launch followed by a gradient launch that reads the winners from here (faster) */
   const uint8_t* ident_arg; /* (B,H,W); only read when winner != NULL */
   /* Optional channel-interleaved copies of the frame stacks, (n_f,H,W,4) = r,g,b,0 per pixel, written by
    * bbd_pack_rgba: one 16-byte load fetches a bilinear tap of all three channels.  When every stack
